@@ -1,0 +1,173 @@
+/*
+ * scpb200.h — C ABI of libscpb200.so: the B200-native (sm_100a) batched replacement for the SCP-QP hot path
+ * of Zhang-Xiaoxue/Senquential-Convex-Programming-for-Trajectory-Planning.
+ *
+ * The reference has no FFI: its boundary for this path is three Python classes (IterClass / MPCclass in
+ * MPC_Iter.py:13-149, SCPcontroller in SCP_controller.py:18-400) called from main.py:123-134.  The Python
+ * facade of this repo keeps those classes and binds the entry points below with ctypes (INTEGRATION.md shows
+ * the stub).  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - Every data pointer is a DEVICE pointer to caller-owned, contiguous memory (FP64 unless stated int32),
+ *     batch outermost, row-major.  The library never allocates caller-visible memory.
+ *   - All work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*); nothing
+ *     synchronises.  `ws` is a caller-provided device workspace of scpb200_workspace_bytes() bytes.
+ *   - Return value: 0 = OK, <0 = argument / launch error (scpb200_last_error() gives the text).
+ *     Per-instance numerical outcomes are DATA (status arrays), not errors.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with SCPB200_ERR_CUDA.
+ *
+ * Index conventions (SCP_controller.py:295,202): n = nVeh*Hp, u[v*Hp + k] (vehicle-major), n1 = n+1 with the
+ * slack omega last (SCP_controller.py:123-127), collision rows ordered (i, j>i, k) then obstacle rows
+ * (v, o, k) (SCP_controller.py:97-114), mc = Hp*(nVeh(nVeh-1)/2 + nVeh*nObst).
+ */
+#ifndef SCPB200_H
+#define SCPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCPB200_VERSION 100
+
+#define SCPB200_OK 0
+#define SCPB200_ERR_ARG (-1)      /* bad dims / null pointer */
+#define SCPB200_ERR_CUDA (-2)     /* CUDA runtime error (no device, launch failure, ...) */
+#define SCPB200_ERR_SIZE (-3)     /* problem does not fit this build's limits */
+
+/* per-instance status bits (scp_solve / qp_solve_dense `status` outputs) */
+#define SCPB200_ST_QP_MAXITER 1   /* some QP hit ipm_max_iter before meeting the tolerances */
+#define SCPB200_ST_QP_PIVOT 2     /* a Cholesky pivot had to be repaired (ill-conditioned normal matrix) */
+#define SCPB200_ST_SCP_MAXITER 4  /* SCP loop ended on max_scp_iter, not on the stop test */
+#define SCPB200_ST_INFEASIBLE 8   /* final iterate violates a collision constraint by more than constraint_tol */
+#define SCPB200_ST_SETUP 16       /* set-up failed for this instance (expm / sampler index) */
+
+typedef struct scpb200_dims {
+    int32_t B;      /* instances (independent scenarios / noise samples) */
+    int32_t nVeh;   /* vehicles per instance (Scenarios.py:59) */
+    int32_t Hp;     /* prediction = control horizon (Scenarios.py:50-51; the reference asserts Hu <= Hp, uses Hu = Hp) */
+    int32_t nObst;  /* obstacles per instance (Scenarios.py:220) */
+    int32_t nPts;   /* points per reference polyline (2 in every shipped scenario) */
+} scpb200_dims;
+
+/* Constants of the path.  scpb200_default_params() fills in the reference's values. */
+typedef struct scpb200_params {
+    double dt;               /* MPC sample time, Scenarios.py:49 (0.4) */
+    double uLim;             /* steering bound, SCP_controller.py:34 (undefined in the reference; = mechanicalSteeringLimit) */
+    double dsafeExtra;       /* Scenarios.py:57 (1.0) */
+    double delta_tol;        /* SCP_controller.py:83 (1e-3) */
+    double omega_weight;     /* SCP_controller.py:84 (1e5) */
+    double omega_ub;         /* SCP_controller.py:85 (1e25; bounds >= inf_bound are treated as absent) */
+    double constraint_tol;   /* Config.py:18 (2*2.1*1e-3) */
+    int32_t max_scp_iter;    /* SCP_controller.py:86 (20) */
+    int32_t obstacle_eval_mode; /* 0: every (v,o,k) once; 1: the reference's nesting (SCP_controller.py:249-263) */
+    /* interior-point controls (the reference delegates these to its third-party solver) */
+    double qp_abstol, qp_reltol, qp_feastol; /* CVXOPT-style stopping rule; defaults 1e-10, 1e-10, 1e-9 */
+    double qp_dual_reg;      /* proximal regularisation of s/z in the normal matrix (default 1e-12) */
+    double inf_bound;        /* |bound| >= inf_bound means "no bound" (default 1e20, Gurobi's convention) */
+    int32_t ipm_max_iter;    /* default 60 */
+    int32_t reserved0;
+    /* extensions, default = reference behaviour */
+    double trust_radius;     /* |u - ubar|_inf <= rho folded into lb/ub; +inf (>= 1e300) = off */
+    double noise_sigma;      /* std-dev of the process noise added to f(x,u)[0:2] (Model.py:84-86: 3e-6); 0 = off */
+    uint64_t seed;           /* Philox4x32-10 key */
+    uint32_t instance0;      /* global index of instance 0 of this call (sharding keeps streams G-independent) */
+    uint32_t noise_counter;  /* draw counter (e.g. the MPC step index) */
+} scpb200_params;
+
+/* width of one row of the per-iteration log of scpb200_scp_solve (SCP_controller.py:169-189, scalar fields) */
+#define SCPB200_LOG_W 10
+/* log row: {slack, SCP_ObjVal (fval+gamma0), QCQP_ObjVal, delta_hat, delta, feasible, max_violation,
+ *           sum_violations, ipm_iterations, qp_status} */
+
+int scpb200_version(void);
+const char *scpb200_last_error(void);
+void scpb200_default_params(scpb200_params *p);
+
+/* number of CUDA devices visible (0 if none); does not create a context on failure */
+int scpb200_device_count(void);
+
+/* bytes of device workspace the solver entry points need for these dims on the current device */
+int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes);
+/* same for scpb200_qp_solve_dense on an arbitrary (n1, mc) */
+int scpb200_qp_workspace_bytes(int32_t n1, int32_t mc, size_t *bytes);
+/* launch geometry scpb200_scp_solve would use (diagnostics): out[5] = {grid, threads, dynamic shared bytes,
+ * normal matrix in shared memory (1/0), SM count} */
+int scpb200_scp_plan(const scpb200_dims *d, int64_t *out);
+
+/*
+ * K1 — replaces MPCclass.__init__ (MPC_Iter.py:57-97): comp_jacobian (Model.py:45-59), discretize
+ * (MPC_Iter.py:99-113), prediction_matrices (:129-149), const_term (:90), mpc_cost_function_matrices
+ * (:116-127), and the reference sampling of IterClass (MPC_Iter.py:35-43 -> SampleReferTraj.py:8-122).
+ *   in : x0[B,nVeh,6] u0[B,nVeh] veh[B,nVeh,5]=(Lf,Lr,Q,Q_final,R) poly[B,nVeh,nPts,2]
+ *   out: ref[B,nVeh,Hp,2]   sampled reference points (ReferenceTrajectoryPoints[k,:,v])
+ *        g[B,nVeh,Hp,2]     impulse response C A^l B      (Mathcal_B[2i:2i+2, j] = g[i-j])
+ *        cterm[B,nVeh,Hp,2] free response (const_term)
+ *        H[B,nVeh,Hp,Hp]    Phi_0      qv[B,nVeh,Hp] Psi_0      gamma0[B] sum_v gamma_0
+ *        abe[B,nVeh,48]     Ad(36) Bd(6) Ed(6), may be NULL   setup_status[B] int32 (0 or SCPB200_ST_SETUP), may be NULL
+ */
+int scpb200_mpc_setup(const scpb200_dims *d, const scpb200_params *p, const double *x0, const double *u0,
+                      const double *veh, const double *poly, double *ref, double *g, double *cterm, double *H,
+                      double *qv, double *gamma0, double *abe, int32_t *setup_status, void *stream);
+
+/*
+ * K2 (materialised) — replaces QCQP_formulate (SCP_controller.py:278-341) + the row assembly of SCP_optimizer
+ * (:93-128): the dense QP the reference hands to its solver, in the reference's layout.
+ *   in : g, cterm, H, qv (K1 outputs), ubar[B,n] linearisation point, dsafe[B,nVeh,nVeh],
+ *        dsafe_obst[B,nVeh,nObst] and obst[B,nObst,Hp,2] (NULL when nObst == 0)
+ *   out: P[B,n1,n1] q[B,n1] A[B,mc,n1] b[B,mc] lb[B,n1] ub[B,n1]
+ */
+int scpb200_assemble_dense(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                           const double *H, const double *qv, const double *ubar, const double *dsafe,
+                           const double *dsafe_obst, const double *obst, double *P, double *q, double *A,
+                           double *b, double *lb, double *ub, void *stream);
+
+/*
+ * a9 — replaces QCQP_evaluate (SCP_controller.py:215-265) (items 3-4 of its return tuple are unused by every
+ * caller and are not produced).   ci[B,nVeh,nVeh,Hp] (symmetric fill, -inf elsewhere) and
+ * ci_obst[B,nVeh,nObst,Hp] may be NULL.
+ */
+int scpb200_qcqp_evaluate(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                          const double *H, const double *qv, const double *gamma0, const double *u,
+                          const double *dsafe, const double *dsafe_obst, const double *obst, double *obj,
+                          double *max_violation, double *sum_violations, int32_t *feasible, double *ci,
+                          double *ci_obst, void *stream);
+
+/*
+ * a11 — replaces forward_U (SCP_controller.py:199-213).  traj[B,Hp,2,nVeh], U[B,Hp,nVeh].
+ */
+int scpb200_forward_u(const scpb200_dims *d, const double *g, const double *cterm, const double *u, double *traj,
+                      double *U, void *stream);
+
+/*
+ * K3 — replaces the third-party QP solve of SCP_controller.py:135-150 on the reference's own dense inputs
+ * (the CVXOPT/Gurobi-replacement entry):   min 1/2 x'Px + q'x  s.t.  A x <= b,  lb <= x <= ub.
+ *   in : n1, mc and P[B,n1,n1] q[B,n1] A[B,mc,n1] b[B,mc] lb[B,n1] ub[B,n1]   (only d->B is read from dims)
+ *   out: x[B,n1] fval[B] (= prob.value) iters[B] int32, status[B] int32, zA[B,mc] multipliers (may be NULL)
+ */
+int scpb200_qp_solve_dense(const scpb200_dims *d, const scpb200_params *p, int32_t n1, int32_t mc,
+                           const double *P, const double *q, const double *A, const double *b, const double *lb,
+                           const double *ub, double *x, double *fval, int32_t *iters, int32_t *status, double *zA,
+                           void *ws, void *stream);
+
+/*
+ * K4 (fused) — replaces SCPcontroller.SCP_controller / SCP_optimizer (SCP_controller.py:40-197): the whole SCP
+ * loop on device, one CTA per instance pulled from a work queue: linearise about ubar, solve the QP with the
+ * CTA-resident interior-point method on the structured rows, evaluate the true QCQP, merit / stop test.
+ *   in : K1 outputs, dsafe, (dsafe_obst, obst), u_inout[B,n] warm start (SCP_controller.py:42-43)
+ *   out: u_inout (solution), traj[B,Hp,2,nVeh], U[B,Hp,nVeh] (forward_U shapes),
+ *        log[B,max_scp_iter,SCPB200_LOG_W] (may be NULL), scp_iters[B] int32 (= QPs solved), ipm_iters[B] int32,
+ *        status[B] int32, obj[B] final QCQP objective, max_violation[B]
+ */
+int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                      const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                      const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                      double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                      double *max_violation, void *ws, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCPB200_H */

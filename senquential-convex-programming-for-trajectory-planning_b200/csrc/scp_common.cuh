@@ -1,0 +1,139 @@
+// scp_common.cuh — execution-model glue shared by every kernel of libscpb200.
+//
+// All CTA-cooperative code in this library is written as a sequence of PHASES: inside a phase each thread
+// works on its own slice of shared memory; phases are separated by a CTA barrier.  The same source is
+// compiled two ways:
+//   * by nvcc for sm_100a — a phase is `{ tid = threadIdx.x; ... } __syncthreads();`
+//   * by g++ for the kernel-logic emulator under tests/emu (CPU tests only, never loaded by the product) —
+//     a phase is a loop over tid, in ascending or descending order (a cheap intra-phase race detector).
+// Warp-level leaf routines (shuffle reductions, the 8x8 tile factorisation) have a device body and a plain
+// sequential host body.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/scpb200.h"
+
+#if defined(__CUDACC__)
+#define SCP_FN __device__ __forceinline__
+#define SCP_MFN __device__ __forceinline__
+#define SCP_HDFN __host__ __device__ __forceinline__
+#define SCP_HDMFN __host__ __device__ __forceinline__
+#define SCP_DEVICE_BUILD 1
+#else
+#define SCP_FN static inline
+#define SCP_MFN inline
+#define SCP_HDFN static inline
+#define SCP_HDMFN inline
+#define SCP_DEVICE_BUILD 0
+#endif
+
+#define SCP_MAX_WARPS 32
+#define SCP_TILE 8
+#define SCP_TILE2 64
+
+// ------------------------------------------------------------------------------------------------ phases
+#if SCP_DEVICE_BUILD
+struct Cta {
+    int nt;
+};
+#define CTA_PHASE(tid) { const int tid = (int)threadIdx.x;
+#define CTA_PHASE_END } __syncthreads();
+#define CTA_RED_BEGIN(cta, nslots)
+#define CTA_PHASE_END_RED(cta, red, nslots) } __syncthreads();
+#else
+#define SCP_EMU_MAXNT 1024
+struct Cta {
+    int nt;
+    int reverse;                           // emulate threads in descending order
+    double part[8 * SCP_EMU_MAXNT];        // per-thread partials of the reduction slots
+    int part_kind[8];                      // 0 = sum, 1 = max
+};
+static inline int scp_emu_tid(const Cta &c, int i) { return c.reverse ? c.nt - 1 - i : i; }
+#define CTA_PHASE(tid) for (int tid##_i = 0; tid##_i < cta.nt; ++tid##_i) { const int tid = scp_emu_tid(cta, tid##_i);
+#define CTA_PHASE_END }
+#define CTA_RED_BEGIN(cta, nslots)                                                     \
+    for (int s_ = 0; s_ < (nslots); ++s_)                                              \
+        for (int t_ = 0; t_ < (cta).nt; ++t_) (cta).part[s_ * SCP_EMU_MAXNT + t_] = 0.0;
+// butterfly in the device's order: v[l] (+|max)= v[l ^ off], off = 16..1; lane 0 of each warp publishes
+#define CTA_PHASE_END_RED(cta, red, nslots)                                            \
+    }                                                                                  \
+    for (int s_ = 0; s_ < (nslots); ++s_)                                              \
+        for (int w_ = 0; w_ < (cta).nt / 32; ++w_) {                                   \
+            double v_[32], n_[32];                                                     \
+            for (int l_ = 0; l_ < 32; ++l_) v_[l_] = (cta).part[s_ * SCP_EMU_MAXNT + w_ * 32 + l_]; \
+            for (int off_ = 16; off_ >= 1; off_ >>= 1) {                               \
+                for (int l_ = 0; l_ < 32; ++l_)                                        \
+                    n_[l_] = (cta).part_kind[s_] ? fmax(v_[l_], v_[l_ ^ off_]) : v_[l_] + v_[l_ ^ off_]; \
+                for (int l_ = 0; l_ < 32; ++l_) v_[l_] = n_[l_];                       \
+            }                                                                          \
+            (red)[s_ * SCP_MAX_WARPS + w_] = v_[0];                                    \
+        }
+#endif
+
+// Inside a reducing phase every thread calls these exactly once per slot (uniform control flow).
+#if SCP_DEVICE_BUILD
+SCP_FN double scp_warp_sum(double v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+SCP_FN double scp_warp_max(double v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+#define CTA_RED_SUM(cta, red, slot, tid, val)                                 \
+    {                                                                         \
+        double r_ = scp_warp_sum(val);                                        \
+        if (((tid) & 31) == 0) (red)[(slot) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
+    }
+#define CTA_RED_MAX(cta, red, slot, tid, val)                                 \
+    {                                                                         \
+        double r_ = scp_warp_max(val);                                        \
+        if (((tid) & 31) == 0) (red)[(slot) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
+    }
+#else
+#define CTA_RED_SUM(cta, red, slot, tid, val) { (cta).part_kind[slot] = 0; (cta).part[(slot) * SCP_EMU_MAXNT + (tid)] = (val); }
+#define CTA_RED_MAX(cta, red, slot, tid, val) { (cta).part_kind[slot] = 1; (cta).part[(slot) * SCP_EMU_MAXNT + (tid)] = (val); }
+#endif
+
+// after the reducing phase: every thread folds the per-warp results (uniform value)
+SCP_FN double cta_red_sum(const Cta &cta, const double *red, int slot)
+{
+    double t = 0.0;
+    const int nw = cta.nt >> 5;
+    for (int w = 0; w < nw; ++w) t += red[slot * SCP_MAX_WARPS + w];
+    return t;
+}
+SCP_FN double cta_red_max(const Cta &cta, const double *red, int slot)
+{
+    double t = red[slot * SCP_MAX_WARPS];
+    const int nw = cta.nt >> 5;
+    for (int w = 1; w < nw; ++w) t = fmax(t, red[slot * SCP_MAX_WARPS + w]);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+SCP_HDFN int scp_imin(int a, int b) { return a < b ? a : b; }
+SCP_HDFN int scp_imax(int a, int b) { return a > b ? a : b; }
+SCP_HDFN int scp_round_up(int a, int m) { return (a + m - 1) / m * m; }
+
+// index of lower-triangular tile (I, J), J <= I, in the tile-packed normal matrix
+SCP_HDFN int scp_tile_off(int I, int J) { return ((I * (I + 1) >> 1) + J) * SCP_TILE2; }
+// element (ci, cj), ci >= cj
+SCP_HDFN int scp_sidx(int ci, int cj)
+{
+    return scp_tile_off(ci >> 3, cj >> 3) + ((ci & 7) << 3) + (cj & 7);
+}
+// t -> (ii, jj) with ii >= jj, t = ii(ii+1)/2 + jj
+SCP_HDFN void scp_tri_decode(int t, int *ii, int *jj)
+{
+    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    *ii = i;
+    *jj = t - i * (i + 1) / 2;
+}

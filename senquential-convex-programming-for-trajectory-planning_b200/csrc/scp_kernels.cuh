@@ -1,0 +1,764 @@
+// scp_kernels.cuh — per-instance device code of the SCP-QP path: set-up (K1), dense assembly (K2), QCQP
+// evaluation, forward prediction and the fused SCP loop (K4).  Written in the phase style of scp_common.cuh so
+// that tests/emu can run the same source on the host.
+#pragma once
+#include "ipm_core.cuh"
+#include "ops_dense.cuh"
+#include "ops_pair.cuh"
+
+// ================================================================================================ Philox
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.  Replaces the np.random.normal draws of Model.py:84-86,
+// whose global MT19937 stream cannot be reproduced in a batched kernel; keyed on (seed; instance, vehicle,
+// counter) so results do not depend on how instances are sharded over GPUs.
+SCP_HDFN void scp_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                uint32_t out[4])
+{
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+SCP_HDFN void scp_noise_pair(uint64_t seed, uint32_t instance, uint32_t vehicle, uint32_t counter, double out[2])
+{
+    uint32_t r[4];
+    scp_philox4x32_10(instance, vehicle, counter, 0x5C9B200u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u1 = ((double)(((uint64_t)r[0] << 21) ^ (r[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u2 = (double)(((uint64_t)r[2] << 21) ^ (r[3] >> 11)) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u1)), ang = 6.283185307179586476925286766559 * u2;
+    out[0] = rad * cos(ang);
+    out[1] = rad * sin(ang);
+}
+
+// ================================================================================================ K1 pieces
+// Model.py:61-87
+SCP_HDFN void scp_bicycle_rhs(const double x[6], double u_ref, double Lf, double Lr, double dx[6])
+{
+    const double L = Lf + Lr, R = Lr / L;
+    const double tu = tan(x[5]);
+    const double v_center = x[3] * sqrt(1.0 + (R * tu) * (R * tu));
+    const double beta = atan(R * tu);
+    dx[0] = v_center * cos(x[2] + beta);
+    dx[1] = v_center * sin(x[2] + beta);
+    dx[2] = v_center * tu * cos(beta) / L;
+    dx[3] = x[4];
+    dx[4] = 0.0;
+    dx[5] = (u_ref - x[5]) / 0.1;
+}
+
+// 8x8 matrix product C = A B (row-major, thread-local)
+SCP_HDFN void scp_mm8(const double *A, const double *B, double *C)
+{
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 8; ++k) acc += A[i * 8 + k] * B[k * 8 + j];
+            C[i * 8 + j] = acc;
+        }
+}
+
+// E = expm(M), 8x8: degree-13 Pade approximant with scaling and squaring (what scipy.linalg.expm runs at
+// MPC_Iter.py:106,111).  Returns 0, or -1 if the Pade denominator is singular.
+SCP_HDFN int scp_expm8(const double *Min, double *E)
+{
+    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                          129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
+                          1323241920.,        40840800.,          960960.,           16380., 182., 1.};
+    double A[64], A2[64], A4[64], A6[64], U[64], V[64], W[64];
+    double nrm = 0.0;
+    for (int j = 0; j < 8; ++j) {
+        double c = 0.0;
+        for (int i = 0; i < 8; ++i) c += fabs(Min[i * 8 + j]);
+        nrm = fmax(nrm, c);
+    }
+    int s = 0;
+    if (nrm > 5.371920351148152) {
+        s = (int)ceil(log2(nrm / 5.371920351148152));
+        if (s < 0) s = 0;
+    }
+    const double sc = ldexp(1.0, -s);
+    for (int i = 0; i < 64; ++i) A[i] = Min[i] * sc;
+    scp_mm8(A, A, A2);
+    scp_mm8(A2, A2, A4);
+    scp_mm8(A4, A2, A6);
+    for (int i = 0; i < 64; ++i) W[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    scp_mm8(A6, W, V);                                   // V used as scratch
+    for (int i = 0; i < 64; ++i) V[i] += b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i];
+    for (int i = 0; i < 8; ++i) V[i * 8 + i] += b[1];
+    scp_mm8(A, V, U);
+    for (int i = 0; i < 64; ++i) W[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    scp_mm8(A6, W, V);
+    for (int i = 0; i < 64; ++i) V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i];
+    for (int i = 0; i < 8; ++i) V[i * 8 + i] += b[0];
+    // solve (V - U) X = (V + U): Gaussian elimination with partial pivoting; Q in A2, R in W
+    for (int i = 0; i < 64; ++i) { A2[i] = V[i] - U[i]; W[i] = V[i] + U[i]; }
+    for (int k = 0; k < 8; ++k) {
+        int piv = k;
+        double best = fabs(A2[k * 8 + k]);
+        for (int i = k + 1; i < 8; ++i)
+            if (fabs(A2[i * 8 + k]) > best) { best = fabs(A2[i * 8 + k]); piv = i; }
+        if (best == 0.0) return -1;
+        if (piv != k)
+            for (int j = 0; j < 8; ++j) {
+                double t = A2[k * 8 + j]; A2[k * 8 + j] = A2[piv * 8 + j]; A2[piv * 8 + j] = t;
+                t = W[k * 8 + j]; W[k * 8 + j] = W[piv * 8 + j]; W[piv * 8 + j] = t;
+            }
+        for (int i = k + 1; i < 8; ++i) {
+            const double l = A2[i * 8 + k] / A2[k * 8 + k];
+            if (l == 0.0) continue;
+            for (int j = k; j < 8; ++j) A2[i * 8 + j] -= l * A2[k * 8 + j];
+            for (int j = 0; j < 8; ++j) W[i * 8 + j] -= l * W[k * 8 + j];
+        }
+    }
+    for (int j = 0; j < 8; ++j)
+        for (int i = 7; i >= 0; --i) {
+            double acc = W[i * 8 + j];
+            for (int k = i + 1; k < 8; ++k) acc -= A2[i * 8 + k] * W[k * 8 + j];
+            W[i * 8 + j] = acc / A2[i * 8 + i];
+        }
+    for (int k = 0; k < s; ++k) {
+        scp_mm8(W, W, V);
+        for (int i = 0; i < 64; ++i) W[i] = V[i];
+    }
+    for (int i = 0; i < 64; ++i) E[i] = W[i];
+    return 0;
+}
+
+// SampleReferTraj.py:81-122
+SCP_HDFN void scp_projection2d(double x1, double y1, double x2, double y2, double x3, double y3, double *xp, double *yp,
+                               double *dist, double *lambda)
+{
+    const double b = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    if (b != 0.0) {
+        const double xn = (x2 - x1) / b, yn = (y2 - y1) / b, x31 = x3 - x1, y31 = y3 - y1;
+        const double dot = xn * x31 + yn * y31;
+        *dist = xn * y31 - yn * x31;
+        *xp = x1 + dot * xn;
+        *yp = y1 + dot * yn;
+        *lambda = dot / b;
+    } else {
+        *dist = sqrt((x3 - x1) * (x3 - x1) + (y3 - y1) * (y3 - y1));
+        *lambda = 0.0;
+        *xp = x1;
+        *yp = y1;
+    }
+}
+
+// SampleReferTraj.py:8-79: projection onto the polyline (first/last pieces extended), then nSamples points at
+// spacing `step`; the trajectory index is never advanced (:26-28), which reproduces the reference's
+// end-of-polyline oscillation.  Returns -1 where the reference would raise IndexError (index_min == nPts).
+SCP_HDFN int scp_sample_reference(int nSamples, int npts, const double *poly, double vx, double vy, double step,
+                                  double *out)
+{
+    double cx = poly[2], cy = poly[3];
+    double sd_min = sqrt((vx - poly[2]) * (vx - poly[2]) + (vy - poly[3]) * (vy - poly[3]));
+    int idx = 2;
+    for (int j = 1; j < npts; ++j) {
+        double xp, yp, sd, lam;
+        scp_projection2d(poly[(j - 1) * 2], poly[(j - 1) * 2 + 1], poly[j * 2], poly[j * 2 + 1], vx, vy, &xp, &yp, &sd,
+                         &lam);
+        if ((0.0 < lam || j == 1) && (lam < 1.0 || j == npts - 1)) {
+            if (fabs(sd) < fabs(sd_min)) { cx = xp; cy = yp; sd_min = sd; idx = j; }
+        } else {   // :69-76 (the reference's '^' at :70 is read as the square it was meant to be)
+            const double ex = vx - poly[j * 2], ey = vy - poly[j * 2 + 1];
+            const double d_end = sqrt(ex * ex + ey * ey);
+            if (fabs(d_end) < fabs(sd_min)) {
+                cx = poly[j * 2]; cy = poly[j * 2 + 1];
+                sd_min = (sd > 0.0 ? 1.0 : (sd < 0.0 ? -1.0 : 0.0)) * d_end;
+                idx = j;
+            }
+        }
+    }
+    if (idx >= npts) return -1;
+    const double dx = poly[idx * 2] - poly[(idx - 1) * 2], dy = poly[idx * 2 + 1] - poly[(idx - 1) * 2 + 1];
+    const double nrm = sqrt(dx * dx + dy * dy);
+    for (int i = 0; i < nSamples; ++i) {
+        const double rx = cx - poly[idx * 2], ry = cy - poly[idx * 2 + 1];
+        const double remaining = sqrt(rx * rx + ry * ry);
+        if (remaining > step) {
+            cx = cx + step * (dx / nrm);
+            cy = cy + step * (dy / nrm);
+        } else {
+            cx = poly[idx * 2] + (step - remaining) * (dx / nrm);
+            cy = poly[idx * 2 + 1] + (step - remaining) * (dy / nrm);
+        }
+        out[i * 2] = cx;
+        out[i * 2 + 1] = cy;
+    }
+    return 0;
+}
+
+// One (instance, vehicle): Model.py:45-59 (Jacobian), MPC_Iter.py:99-113 (ZOH via expm; both of the
+// reference's 7x7 exponentials come out of one 8x8 exponential of dt*[[Ac,Bc,Ec],[0,0,0]]), :129-149
+// (prediction recurrences), :35-43 (reference sampling).  Returns 0 or SCPB200_ST_SETUP.
+SCP_HDFN int scp_setup_vehicle(int Hp, int nPts, double dt, const double *x, double u0, const double *pv,
+                               const double *poly, const double *noise, double *ref, double *g, double *cterm,
+                               double *abe)
+{
+    const double Lf = pv[0], Lr = pv[1], Ls = Lf + Lr;
+    const double t5 = tan(x[5]);
+    const double w = sqrt((Lr * Lr * t5 * t5) / (Ls * Ls) + 1.0);
+    const double ang = x[2] + atan((Lr * t5) / Ls);
+    const double sa = sin(ang), ca = cos(ang), sec2 = t5 * t5 + 1.0;
+    double M[64], E[64];
+    for (int i = 0; i < 64; ++i) M[i] = 0.0;
+    M[0 * 8 + 2] = -x[3] * sa * w;
+    M[0 * 8 + 3] = ca * w;
+    M[0 * 8 + 5] = (Lr * Lr * x[3] * ca * t5 * sec2) / (w * Ls * Ls) - (Lr * x[3] * sa * sec2) / (w * Ls);
+    M[1 * 8 + 2] = x[3] * ca * w;
+    M[1 * 8 + 3] = sa * w;
+    M[1 * 8 + 5] = (Lr * x[3] * ca * sec2) / (w * Ls) + (Lr * Lr * x[3] * sa * t5 * sec2) / (w * Ls * Ls);
+    M[2 * 8 + 3] = t5 / Ls;
+    M[2 * 8 + 5] = (x[3] * sec2) / Ls;
+    M[3 * 8 + 4] = 1.0;
+    M[5 * 8 + 5] = -10.0;
+    M[5 * 8 + 6] = 10.0;                                    // Bc
+    double f[6];
+    scp_bicycle_rhs(x, u0, Lf, Lr, f);
+    if (noise) { f[0] += noise[0]; f[1] += noise[1]; }
+    for (int i = 0; i < 6; ++i) {                           // Ec = f - Ac x - Bc u  (Model.py:58)
+        double acc = f[i];
+        for (int j = 0; j < 6; ++j) acc -= M[i * 8 + j] * x[j];
+        M[i * 8 + 7] = acc - M[i * 8 + 6] * u0;
+    }
+    for (int i = 0; i < 64; ++i) M[i] *= dt;
+    int rc = 0;
+    if (scp_expm8(M, E)) rc = SCPB200_ST_SETUP;
+    double Ad[36], Bd[6], Ed[6];
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) Ad[i * 6 + j] = E[i * 8 + j];
+        Bd[i] = E[i * 8 + 6];
+        Ed[i] = fabs(E[i * 8 + 7]) <= 1e-30 ? 0.0 : E[i * 8 + 7];      // MPC_Iter.py:87
+    }
+    if (abe) {
+        for (int i = 0; i < 36; ++i) abe[i] = Ad[i];
+        for (int i = 0; i < 6; ++i) { abe[36 + i] = Bd[i]; abe[42 + i] = Ed[i]; }
+    }
+    if (scp_sample_reference(Hp, nPts, poly, x[0], x[1], x[3] * dt, ref)) rc = SCPB200_ST_SETUP;
+    double CA[12], Sm[12], Tm[12];
+    for (int i = 0; i < 12; ++i) { CA[i] = 0.0; Sm[i] = 0.0; }
+    CA[0] = 1.0;
+    CA[7] = 1.0;
+    for (int k = 0; k < Hp; ++k) {
+        for (int r = 0; r < 2; ++r) {
+            double acc = 0.0;
+            for (int j = 0; j < 6; ++j) acc += CA[r * 6 + j] * Bd[j];
+            g[k * 2 + r] = acc;
+        }
+        for (int i = 0; i < 12; ++i) Sm[i] += CA[i];
+        for (int r = 0; r < 2; ++r)
+            for (int j = 0; j < 6; ++j) {
+                double acc = 0.0;
+                for (int l = 0; l < 6; ++l) acc += CA[r * 6 + l] * Ad[l * 6 + j];
+                Tm[r * 6 + j] = acc;
+            }
+        for (int i = 0; i < 12; ++i) CA[i] = Tm[i];
+        for (int r = 0; r < 2; ++r) {
+            double acc = 0.0, acc2 = 0.0;
+            for (int j = 0; j < 6; ++j) { acc += CA[r * 6 + j] * x[j]; acc2 += Sm[r * 6 + j] * Ed[j]; }
+            cterm[k * 2 + r] = acc + acc2;
+        }
+    }
+    return rc;
+}
+
+// K1, one CTA per instance: phase 1 one thread per vehicle (serial expm/recurrences), phase 2 all threads on
+// the cost matrices of MPC_Iter.py:116-127:  H = B'QB + R,  qv = -2 B'Q(Ref - c),  gamma0 = sum_v Err'Q Err.
+SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const double *x0,
+                               const double *u0, const double *veh, const double *poly, double *ref, double *g,
+                               double *cterm, double *H, double *qv, double *gamma0, double *abe,
+                               int32_t *setup_status, double *red, int *flag)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp, nPts = d.nPts;
+    CTA_PHASE(tid)
+        if (tid == 0) *flag = 0;
+    CTA_PHASE_END
+    CTA_PHASE(tid)
+        for (int v = tid; v < nVeh; v += cta.nt) {
+            const size_t iv = (size_t)b * nVeh + v;
+            double nz[2];
+            const double *noise = 0;
+            if (p.noise_sigma > 0.0) {
+                scp_noise_pair(p.seed, p.instance0 + (uint32_t)b, (uint32_t)v, p.noise_counter, nz);
+                nz[0] *= p.noise_sigma;
+                nz[1] *= p.noise_sigma;
+                noise = nz;
+            }
+            const int rc = scp_setup_vehicle(Hp, nPts, p.dt, x0 + iv * 6, u0[iv], veh + iv * 5, poly + iv * nPts * 2,
+                                             noise, ref + iv * Hp * 2, g + iv * Hp * 2, cterm + iv * Hp * 2,
+                                             abe ? abe + iv * 48 : 0);
+            if (rc) *flag = rc;
+        }
+    CTA_PHASE_END
+    CTA_RED_BEGIN(cta, 1)
+    CTA_PHASE(tid)
+        double gam = 0.0;
+        for (int e = tid; e < nVeh * Hp * Hp; e += cta.nt) {
+            const int v = e / (Hp * Hp), a = (e / Hp) % Hp, bb = e % Hp;
+            const size_t iv = (size_t)b * nVeh + v;
+            const double *gv = g + iv * Hp * 2;
+            const double Q = veh[iv * 5 + 2], Qf = veh[iv * 5 + 3], R = veh[iv * 5 + 4];
+            double acc = 0.0;
+            for (int i = (a > bb ? a : bb); i < Hp; ++i) {
+                const double wq = (i == Hp - 1) ? Qf : Q;
+                acc += wq * (gv[(i - a) * 2] * gv[(i - bb) * 2] + gv[(i - a) * 2 + 1] * gv[(i - bb) * 2 + 1]);
+            }
+            H[iv * Hp * Hp + a * Hp + bb] = acc + (a == bb ? R : 0.0);
+        }
+        for (int c = tid; c < nVeh * Hp; c += cta.nt) {
+            const int v = c / Hp, a = c - v * Hp;
+            const size_t iv = (size_t)b * nVeh + v;
+            const double *gv = g + iv * Hp * 2, *cv = cterm + iv * Hp * 2, *rv = ref + iv * Hp * 2;
+            const double Q = veh[iv * 5 + 2], Qf = veh[iv * 5 + 3];
+            double acc = 0.0;
+            for (int i = a; i < Hp; ++i) {
+                const double wq = (i == Hp - 1) ? Qf : Q;
+                acc += wq * (gv[(i - a) * 2] * (rv[i * 2] - cv[i * 2]) + gv[(i - a) * 2 + 1] * (rv[i * 2 + 1] - cv[i * 2 + 1]));
+            }
+            qv[iv * Hp + a] = -2.0 * acc;
+            const double wq = (a == Hp - 1) ? Qf : Q;
+            const double ex = rv[a * 2] - cv[a * 2], ey = rv[a * 2 + 1] - cv[a * 2 + 1];
+            gam += wq * (ex * ex + ey * ey);
+        }
+        CTA_RED_SUM(cta, red, 0, tid, gam)
+    CTA_PHASE_END_RED(cta, red, 1)
+    const double gam = cta_red_sum(cta, red, 0);
+    CTA_PHASE(tid)
+        if (tid == 0) {
+            gamma0[b] = gam;
+            if (setup_status) setup_status[b] = *flag;
+        }
+    CTA_PHASE_END
+}
+
+// ================================================================================================ shared pieces
+// pos[(v,k)] = cterm_v(k) + sum_{a<=k} g_v[k-a] u_v[a]      (forward_U, SCP_controller.py:199-213)
+SCP_FN void scp_positions(Cta &cta, int nVeh, int Hp, const double *g, const double *cterm, const double *u, double *pos)
+{
+    CTA_PHASE(tid)
+        for (int c = tid; c < nVeh * Hp; c += cta.nt) {
+            const int v = c / Hp, k = c - v * Hp;
+            const double *gv = g + (size_t)v * Hp * 2;
+            double px = cterm[c * 2], py = cterm[c * 2 + 1];
+            for (int a = 0; a <= k; ++a) {
+                px += gv[(k - a) * 2] * u[v * Hp + a];
+                py += gv[(k - a) * 2 + 1] * u[v * Hp + a];
+            }
+            pos[c * 2] = px;
+            pos[c * 2 + 1] = py;
+        }
+    CTA_PHASE_END
+}
+
+SCP_FN void scp_row_decode(int nVeh, int Hp, int nObst, int mcv, int r, int *i, int *j, int *o, int *k)
+{
+    if (r < mcv) {
+        const int p = r / Hp;
+        *k = r - p * Hp;
+        int ii = 0, rem = p;
+        while (rem >= nVeh - 1 - ii) { rem -= nVeh - 1 - ii; ++ii; }
+        *i = ii; *j = ii + 1 + rem; *o = -1;
+    } else {
+        const int q = r - mcv;
+        *i = q / (nObst * Hp); *o = (q / Hp) % nObst; *k = q % Hp; *j = -1;
+    }
+}
+
+struct ScpEval {
+    double obj, max_violation, sum_violations;
+    int feasible;
+};
+
+// QCQP_evaluate (SCP_controller.py:215-265) for one instance.  `pos` is [n][2] scratch, `red` reduction scratch.
+// obstacle_mode 1 reproduces the reference's nesting of the obstacle loop inside the v2 loop (:249-263).
+SCP_FN void scp_evaluate(Cta &cta, int nVeh, int Hp, int nObst, const double *g, const double *cterm, const double *H,
+                         const double *qv, double gamma0, const double *u, const double *dsafe,
+                         const double *dsafe_obst, const double *obst, double dsafeExtra, double tol,
+                         int obstacle_mode, double *pos, double *red, ScpEval *out, double *ci_out, double *cio_out)
+{
+    const int n = nVeh * Hp, mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    scp_positions(cta, nVeh, Hp, g, cterm, u, pos);
+    CTA_RED_BEGIN(cta, 3)
+    CTA_PHASE(tid)
+        double po = 0.0, ps = 0.0, pm = 0.0;
+        for (int c = tid; c < n; c += cta.nt) {
+            const int v = c / Hp;
+            const double *Hr = H + (size_t)c * Hp;
+            double acc = 0.0;
+            for (int bb = 0; bb < Hp; ++bb) acc += Hr[bb] * u[v * Hp + bb];
+            po += u[c] * (acc + qv[c]);
+        }
+        if (ci_out)
+            for (int e = tid; e < nVeh * nVeh * Hp; e += cta.nt) {
+                const int i = e / (nVeh * Hp), j = (e / Hp) % nVeh;
+                if (i == j) ci_out[e] = -INFINITY;
+            }
+        for (int r = tid; r < mc; r += cta.nt) {
+            int i, j, o, k;
+            scp_row_decode(nVeh, Hp, nObst, mcv, r, &i, &j, &o, &k);
+            double dx, dy, sbar;
+            int mult = 1;
+            if (o < 0) {
+                dx = pos[(i * Hp + k) * 2] - pos[(j * Hp + k) * 2];
+                dy = pos[(i * Hp + k) * 2 + 1] - pos[(j * Hp + k) * 2 + 1];
+                sbar = dsafe[i * nVeh + j] + dsafeExtra;
+            } else {
+                dx = pos[(i * Hp + k) * 2] - obst[(o * Hp + k) * 2];
+                dy = pos[(i * Hp + k) * 2 + 1] - obst[(o * Hp + k) * 2 + 1];
+                sbar = dsafe_obst[i * nObst + o] + dsafeExtra;
+                if (obstacle_mode == 1) mult = nVeh - 1 - i;
+            }
+            const double ci = sbar * sbar - (dx * dx + dy * dy);
+            if (o < 0) {
+                if (ci_out) { ci_out[(i * nVeh + j) * Hp + k] = ci; ci_out[(j * nVeh + i) * Hp + k] = ci; }
+            } else if (cio_out) {
+                cio_out[(i * nObst + o) * Hp + k] = (mult > 0) ? ci : -INFINITY;
+            }
+            if (ci > tol && mult > 0) { ps += mult * ci; pm = fmax(pm, ci); }
+        }
+        CTA_RED_SUM(cta, red, 0, tid, po)
+        CTA_RED_SUM(cta, red, 1, tid, ps)
+        CTA_RED_MAX(cta, red, 2, tid, pm)
+    CTA_PHASE_END_RED(cta, red, 3)
+    out->obj = cta_red_sum(cta, red, 0) + gamma0;
+    out->sum_violations = cta_red_sum(cta, red, 1);
+    out->max_violation = cta_red_max(cta, red, 2);
+    out->feasible = out->max_violation > 0.0 ? 0 : 1;
+}
+
+// Linearisation about ubar (SCP_controller.py:97-114 through the structured identity of ops_pair.cuh):
+// dbar[r] = relative position at ubar, bA[r] = -sbar^2 - |dbar|^2 + 2 dbar.(c_i(k) - c_j(k)).
+SCP_FN void scp_linearise(Cta &cta, int nVeh, int Hp, int nObst, const double *g, const double *cterm,
+                          const double *ubar, const double *dsafe, const double *dsafe_obst, const double *obst,
+                          double dsafeExtra, double *pos, double *dbar, double *bA)
+{
+    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    scp_positions(cta, nVeh, Hp, g, cterm, ubar, pos);
+    CTA_PHASE(tid)
+        for (int r = tid; r < mc; r += cta.nt) {
+            int i, j, o, k;
+            scp_row_decode(nVeh, Hp, nObst, mcv, r, &i, &j, &o, &k);
+            double dx, dy, bx, by, sbar;
+            if (o < 0) {
+                dx = pos[(i * Hp + k) * 2] - pos[(j * Hp + k) * 2];
+                dy = pos[(i * Hp + k) * 2 + 1] - pos[(j * Hp + k) * 2 + 1];
+                bx = cterm[(i * Hp + k) * 2] - cterm[(j * Hp + k) * 2];
+                by = cterm[(i * Hp + k) * 2 + 1] - cterm[(j * Hp + k) * 2 + 1];
+                sbar = dsafe[i * nVeh + j] + dsafeExtra;
+            } else {
+                const double ox = obst[(o * Hp + k) * 2], oy = obst[(o * Hp + k) * 2 + 1];
+                dx = pos[(i * Hp + k) * 2] - ox;
+                dy = pos[(i * Hp + k) * 2 + 1] - oy;
+                bx = cterm[(i * Hp + k) * 2] - ox;
+                by = cterm[(i * Hp + k) * 2 + 1] - oy;
+                sbar = dsafe_obst[i * nObst + o] + dsafeExtra;
+            }
+            dbar[r * 2] = dx;
+            dbar[r * 2 + 1] = dy;
+            bA[r] = -sbar * sbar - (dx * dx + dy * dy) + 2.0 * (dx * bx + dy * by);
+        }
+    CTA_PHASE_END
+}
+
+// ================================================================================================ working set
+struct ScpBump {
+    double *base;
+    size_t off;
+    SCP_HDMFN double *take(size_t nd)
+    {
+        double *p = base ? base + off : 0;
+        off += (nd + 1) & ~(size_t)1;      // keep 16-byte alignment
+        return p;
+    }
+};
+
+// Carve the interior-point working set out of `sh` (shared memory); S comes from `Sglobal` when it does not fit.
+SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, double *Sglobal, bool S_in_shared)
+{
+    m.n1 = n1; m.n1p = scp_round_up(n1, SCP_TILE); m.T = m.n1p / SCP_TILE; m.mc = mc;
+    const size_t Sd = (size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2;
+    m.S = S_in_shared ? bp.take(Sd) : Sglobal;
+    m.Linv = bp.take((size_t)m.T * SCP_TILE2);
+    m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
+    m.bA = bp.take(mc); m.sA = bp.take(mc); m.zA = bp.take(mc); m.rzA = bp.take(mc);
+    m.dsA = bp.take(mc); m.dzA = bp.take(mc); m.ccA = bp.take(mc);
+    m.ub = bp.take(m.n1p); m.sU = bp.take(m.n1p); m.zU = bp.take(m.n1p); m.dsU = bp.take(m.n1p);
+    m.dzU = bp.take(m.n1p); m.ccU = bp.take(m.n1p);
+    m.lb = bp.take(m.n1p); m.sL = bp.take(m.n1p); m.zL = bp.take(m.n1p); m.dsL = bp.take(m.n1p);
+    m.dzL = bp.take(m.n1p); m.ccL = bp.take(m.n1p);
+    m.red = bp.take(8 * SCP_MAX_WARPS);
+    m.t8 = bp.take(16);
+}
+
+SCP_HDFN size_t ipm_S_doubles(int n1)
+{
+    const int T = scp_round_up(n1, SCP_TILE) / SCP_TILE;
+    return (size_t)(T * (T + 1) / 2) * SCP_TILE2;
+}
+
+SCP_HDFN size_t ipm_shared_doubles(int n1, int mc, bool S_in_shared)
+{
+    ScpBump bp = {0, 0};
+    IpmMem m;
+    ipm_carve(bp, m, n1, mc, 0, S_in_shared);
+    return bp.off;
+}
+
+struct ScpMem {
+    IpmMem ipm;
+    double *g, *dbar, *resp, *ucur;
+};
+
+SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, double *Sglobal, bool S_in_shared)
+{
+    const int n = nVeh * Hp, mc = Hp * (nVeh * (nVeh - 1) / 2 + nVeh * nObst);
+    ipm_carve(bp, s.ipm, n + 1, mc, Sglobal, S_in_shared);
+    s.g = bp.take((size_t)n * 2);
+    s.dbar = bp.take((size_t)mc * 2);
+    s.resp = bp.take((size_t)n * 2);
+    s.ucur = bp.take(s.ipm.n1p);
+}
+
+SCP_HDFN size_t scp_shared_doubles(int nVeh, int Hp, int nObst, bool S_in_shared)
+{
+    ScpBump bp = {0, 0};
+    ScpMem s;
+    scp_carve(bp, s, nVeh, Hp, nObst, 0, S_in_shared);
+    return bp.off;
+}
+
+// ================================================================================================ K4: the SCP loop
+struct ScpIO {
+    const double *g, *cterm, *H, *qv, *gamma0, *dsafe, *dsafe_obst, *obst;   // batch base pointers
+    double *u, *traj, *U, *log, *obj, *max_violation;
+    int32_t *scp_iters, *ipm_iters, *status;
+};
+
+// SCP_optimizer (SCP_controller.py:74-197) + the result shaping of SCP_controller (:68-70) for instance b.
+SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const ScpIO &io,
+                               ScpMem &s)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp;
+    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    IpmMem &m = s.ipm;
+    const double *gB = io.g + (size_t)b * n * 2, *cB = io.cterm + (size_t)b * n * 2;
+    const double *HB = io.H + (size_t)b * n * Hp, *qB = io.qv + (size_t)b * n;
+    const double *dsB = io.dsafe + (size_t)b * nVeh * nVeh;
+    const double *dsoB = nObst ? io.dsafe_obst + (size_t)b * nVeh * nObst : 0;
+    const double *obB = nObst ? io.obst + (size_t)b * nObst * Hp * 2 : 0;
+    const double gamma0 = io.gamma0[b];
+    double *uB = io.u + (size_t)b * n;
+
+    IpmCtl ctl;
+    ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
+    ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+
+    PairOp op;
+    op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
+    op.g = s.g; op.H = HB; op.dbar = s.dbar; op.resp = s.resp; op.red = m.red;
+
+    // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
+    CTA_PHASE(tid)
+        for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = gB[e];
+        for (int c = tid; c < m.n1p; c += cta.nt) {
+            double uv = 0.0;
+            if (c < n) {
+                uv = uB[c];
+                if (c == 0 && fabs(uv) < 2.220446049250313e-16) uv = 2.220446049250313e-16;
+            }
+            s.ucur[c] = uv;
+            m.q[c] = (c < n) ? qB[c] : (c == n ? p.omega_weight : 0.0);
+        }
+    CTA_PHASE_END
+
+    ScpEval ev;
+    scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra, p.constraint_tol,
+                 p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
+    double obj0 = ev.obj, mv0 = ev.max_violation;
+    int it = 0, ipm_total = 0, st = 0, stopped = 0;
+    for (it = 0; it < p.max_scp_iter; ++it) {
+        scp_linearise(cta, nVeh, Hp, nObst, s.g, cB, s.ucur, dsB, dsoB, obB, p.dsafeExtra, s.resp, s.dbar, m.bA);
+        CTA_PHASE(tid)
+            for (int c = tid; c < m.n1p; c += cta.nt) {
+                double lo = -p.uLim, hi = p.uLim;
+                if (c < n) {
+                    if (p.trust_radius < 1e300) {
+                        lo = fmax(lo, s.ucur[c] - p.trust_radius);
+                        hi = fmin(hi, s.ucur[c] + p.trust_radius);
+                    }
+                } else if (c == n) { lo = 0.0; hi = p.omega_ub; }
+                m.lb[c] = lo;
+                m.ub[c] = hi;
+            }
+        CTA_PHASE_END
+        IpmResult res;
+        ipm_solve(cta, op, m, ctl, &res);
+        ipm_total += res.iters;
+        if (res.status & SCPB200_ST_QP_MAXITER) st |= SCPB200_ST_QP_MAXITER;
+        if (res.status & SCPB200_ST_QP_PIVOT) st |= SCPB200_ST_QP_PIVOT;
+        const double slack = m.x[n];
+        CTA_PHASE(tid)
+            for (int c = tid; c < n; c += cta.nt) s.ucur[c] = m.x[c];
+        CTA_PHASE_END
+        scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra,
+                     p.constraint_tol, p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
+        const double fval = res.fval + gamma0;
+        const double merit0 = obj0 + p.omega_weight * mv0;
+        const double delta_hat = merit0 - fval;
+        const double delta = merit0 - (ev.obj + p.omega_weight * ev.max_violation);
+        obj0 = ev.obj;
+        mv0 = ev.max_violation;
+        if (io.log) {
+            CTA_PHASE(tid)
+                if (tid == 0) {
+                    double *L = io.log + ((size_t)b * p.max_scp_iter + it) * SCPB200_LOG_W;
+                    L[0] = slack; L[1] = fval; L[2] = ev.obj; L[3] = delta_hat; L[4] = delta; L[5] = ev.feasible;
+                    L[6] = ev.max_violation; L[7] = ev.sum_violations; L[8] = res.iters; L[9] = res.status;
+                }
+            CTA_PHASE_END
+        }
+        if (nVeh == 1 && fabs(delta) < p.delta_tol && ev.max_violation > p.constraint_tol) { ++it; stopped = 1; break; }
+        if (fabs(delta) < p.delta_tol && ev.max_violation <= p.constraint_tol) { ++it; stopped = 1; break; }
+    }
+    if (!stopped) st |= SCPB200_ST_SCP_MAXITER;
+    if (!ev.feasible) st |= SCPB200_ST_INFEASIBLE;
+    // results: u, forward_U shapes traj[Hp][2][nVeh], U[Hp][nVeh]
+    scp_positions(cta, nVeh, Hp, s.g, cB, s.ucur, s.resp);
+    CTA_PHASE(tid)
+        for (int c = tid; c < n; c += cta.nt) {
+            const int v = c / Hp, k = c - v * Hp;
+            uB[c] = s.ucur[c];
+            if (io.U) io.U[((size_t)b * Hp + k) * nVeh + v] = s.ucur[c];
+            if (io.traj) {
+                io.traj[(((size_t)b * Hp + k) * 2 + 0) * nVeh + v] = s.resp[c * 2];
+                io.traj[(((size_t)b * Hp + k) * 2 + 1) * nVeh + v] = s.resp[c * 2 + 1];
+            }
+        }
+        if (tid == 0) {
+            if (io.scp_iters) io.scp_iters[b] = it;
+            if (io.ipm_iters) io.ipm_iters[b] = ipm_total;
+            if (io.status) io.status[b] = st;
+            if (io.obj) io.obj[b] = ev.obj;
+            if (io.max_violation) io.max_violation[b] = ev.max_violation;
+        }
+    CTA_PHASE_END
+}
+
+// ================================================================================================ K3: dense QP
+struct QpIO {
+    const double *P, *q, *A, *b, *lb, *ub;
+    double *x, *fval, *zA;
+    int32_t *iters, *status;
+};
+
+SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc, int b, const QpIO &io, IpmMem &m)
+{
+    IpmCtl ctl;
+    ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
+    ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+    DenseOp op;
+    op.n1 = n1; op.mc = mc;
+    op.P = io.P + (size_t)b * n1 * n1;
+    op.A = io.A + (size_t)b * mc * n1;
+    CTA_PHASE(tid)
+        for (int c = tid; c < m.n1p; c += cta.nt) {
+            m.q[c] = c < n1 ? io.q[(size_t)b * n1 + c] : 0.0;
+            m.ub[c] = c < n1 ? io.ub[(size_t)b * n1 + c] : 1e300;
+            m.lb[c] = c < n1 ? io.lb[(size_t)b * n1 + c] : -1e300;
+        }
+        for (int r = tid; r < mc; r += cta.nt) m.bA[r] = io.b[(size_t)b * mc + r];
+    CTA_PHASE_END
+    IpmResult res;
+    ipm_solve(cta, op, m, ctl, &res);
+    CTA_PHASE(tid)
+        for (int c = tid; c < n1; c += cta.nt) io.x[(size_t)b * n1 + c] = m.x[c];
+        if (io.zA)
+            for (int r = tid; r < mc; r += cta.nt) io.zA[(size_t)b * mc + r] = m.zA[r];
+        if (tid == 0) {
+            io.fval[b] = res.fval;
+            if (io.iters) io.iters[b] = res.iters;
+            if (io.status) io.status[b] = res.status;
+        }
+    CTA_PHASE_END
+}
+
+// ================================================================================================ K2: dense assembly
+// One CTA per instance: linearise about ubar, then stream the dense QP of SCP_controller.py:93-128 to HBM in
+// the reference's layout.  sh: pos[n][2], dbar[mc][2], bA[mc], g[n][2], ubar[n].
+SCP_FN void scp_assemble_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const double *g,
+                                  const double *cterm, const double *H, const double *qv, const double *ubar,
+                                  const double *dsafe, const double *dsafe_obst, const double *obst, double *P,
+                                  double *q, double *A, double *bvec, double *lb, double *ub, double *sh)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp, n1 = n + 1;
+    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    ScpBump bp = {sh, 0};
+    double *pos = bp.take((size_t)n * 2), *dbar = bp.take((size_t)mc * 2), *bA = bp.take(mc);
+    double *gs = bp.take((size_t)n * 2), *us = bp.take(n);
+    const double *gB = g + (size_t)b * n * 2, *cB = cterm + (size_t)b * n * 2;
+    const double *HB = H + (size_t)b * n * Hp;
+    CTA_PHASE(tid)
+        for (int e = tid; e < n * 2; e += cta.nt) gs[e] = gB[e];
+        for (int c = tid; c < n; c += cta.nt) us[c] = ubar[(size_t)b * n + c];
+    CTA_PHASE_END
+    scp_linearise(cta, nVeh, Hp, nObst, gs, cB, us, dsafe + (size_t)b * nVeh * nVeh,
+                  nObst ? dsafe_obst + (size_t)b * nVeh * nObst : 0, nObst ? obst + (size_t)b * nObst * Hp * 2 : 0,
+                  p.dsafeExtra, pos, dbar, bA);
+    CTA_PHASE(tid)
+        // q, lb, ub, b
+        double *qB = q + (size_t)b * n1, *lbB = lb + (size_t)b * n1, *ubB = ub + (size_t)b * n1;
+        for (int c = tid; c < n1; c += cta.nt) {
+            double lo = -p.uLim, hi = p.uLim;
+            if (c < n) {
+                if (p.trust_radius < 1e300) { lo = fmax(lo, us[c] - p.trust_radius); hi = fmin(hi, us[c] + p.trust_radius); }
+                qB[c] = qv[(size_t)b * n + c];
+            } else { lo = 0.0; hi = p.omega_ub; qB[c] = p.omega_weight; }
+            lbB[c] = lo;
+            ubB[c] = hi;
+        }
+        for (int r = tid; r < mc; r += cta.nt) bvec[(size_t)b * mc + r] = bA[r];
+        // P = blkdiag(2 H, 0): flat, coalesced
+        double *PB = P + (size_t)b * n1 * n1;
+        {
+            int row = tid / n1, col = tid - row * n1;
+            const int drow = cta.nt / n1, dcol = cta.nt - drow * n1;
+            for (int e = tid; e < n1 * n1; e += cta.nt) {
+                double val = 0.0;
+                if (row < n && col < n) {
+                    const int v = row / Hp;
+                    if (col >= v * Hp && col < (v + 1) * Hp) val = 2.0 * HB[(size_t)row * Hp + (col - v * Hp)];
+                }
+                PB[e] = val;
+                row += drow; col += dcol;
+                if (col >= n1) { col -= n1; ++row; }
+            }
+        }
+        // A: flat, coalesced; row meta from shared
+        double *AB = A + (size_t)b * mc * n1;
+        {
+            int row = tid / n1, col = tid - row * n1;
+            const int drow = cta.nt / n1, dcol = cta.nt - drow * n1;
+            for (size_t e = tid; e < (size_t)mc * n1; e += cta.nt) {
+                double val = 0.0;
+                if (col == n) val = -1.0;
+                else {
+                    int i, j, o, k;
+                    scp_row_decode(nVeh, Hp, nObst, mcv, row, &i, &j, &o, &k);
+                    const int v = col / Hp, a = col - v * Hp;
+                    if (a <= k && (v == i || v == j)) {
+                        const double cf = 2.0 * (dbar[row * 2] * gs[(v * Hp + k - a) * 2] + dbar[row * 2 + 1] * gs[(v * Hp + k - a) * 2 + 1]);
+                        val = (v == i) ? -cf : cf;
+                        if (fabs(val) <= 1e-20) val = 0.0;               // SCP_controller.py:128
+                    }
+                }
+                AB[e] = val;
+                row += drow; col += dcol;
+                if (col >= n1) { col -= n1; ++row; }
+            }
+        }
+    CTA_PHASE_END
+}

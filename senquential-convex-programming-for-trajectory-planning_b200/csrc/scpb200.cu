@@ -1,0 +1,440 @@
+// scpb200.cu — __global__ kernels and the extern "C" entry points of libscpb200.so (include/scpb200.h).
+// sm_100a only.  No torch types, no host fallback: every compute entry fails with SCPB200_ERR_CUDA when the
+// CUDA runtime reports an error (e.g. no device).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "scp_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CUDA_TRY(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) return set_err(SCPB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int scpb200_version(void) { return SCPB200_VERSION; }
+extern "C" const char *scpb200_last_error(void) { return g_err; }
+
+extern "C" void scpb200_default_params(scpb200_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->dt = 0.4;
+    p->uLim = 3.0 * 3.14159265358979323846 / 180.0;
+    p->dsafeExtra = 1.0;
+    p->delta_tol = 1e-3;
+    p->omega_weight = 1e5;
+    p->omega_ub = 1e25;
+    p->constraint_tol = 2 * 2.1 * 1e-3;
+    p->max_scp_iter = 20;
+    p->obstacle_eval_mode = 0;
+    p->qp_abstol = 1e-10;
+    p->qp_reltol = 1e-10;
+    p->qp_feastol = 1e-9;
+    p->qp_dual_reg = 1e-12;
+    p->inf_bound = 1e20;
+    p->ipm_max_iter = 60;
+    p->trust_radius = 1e308;
+    p->noise_sigma = 0.0;
+    p->seed = 0;
+    p->instance0 = 0;
+    p->noise_counter = 0;
+}
+
+extern "C" int scpb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ device info
+struct DevInfo {
+    int sms, smem_optin;
+};
+static int dev_info(DevInfo *di)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di->sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+static int check_dims(const scpb200_dims *d)
+{
+    if (!d) return set_err(SCPB200_ERR_ARG, "dims is NULL");
+    if (d->B < 0 || d->nVeh < 1 || d->Hp < 1 || d->nObst < 0 || d->nPts < 2)
+        return set_err(SCPB200_ERR_ARG, "bad dims (need B>=0, nVeh>=1, Hp>=1, nObst>=0, nPts>=2)");
+    if (d->nVeh == 1 && d->nObst == 0) return set_err(SCPB200_ERR_ARG, "no constraint rows (nVeh==1 and nObst==0)");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_mpc_setup(scpb200_dims d, scpb200_params p, const double *x0, const double *u0,
+                                                   const double *veh, const double *poly, double *ref, double *g,
+                                                   double *cterm, double *H, double *qv, double *gamma0, double *abe,
+                                                   int32_t *setup_status)
+{
+    __shared__ double red[8 * SCP_MAX_WARPS];
+    __shared__ int flag;
+    Cta cta = {(int)blockDim.x};
+    for (int b = blockIdx.x; b < d.B; b += gridDim.x)
+        scp_setup_instance(cta, d, p, b, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe, setup_status, red, &flag);
+}
+
+__global__ void __launch_bounds__(256) k_assemble(scpb200_dims d, scpb200_params p, const double *g, const double *cterm,
+                                                  const double *H, const double *qv, const double *ubar,
+                                                  const double *dsafe, const double *dsafe_obst, const double *obst,
+                                                  double *P, double *q, double *A, double *bvec, double *lb, double *ub)
+{
+    extern __shared__ double sh[];
+    Cta cta = {(int)blockDim.x};
+    for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+        scp_assemble_instance(cta, d, p, b, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, bvec, lb, ub, sh);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_evaluate(scpb200_dims d, scpb200_params p, const double *g, const double *cterm,
+                                                  const double *H, const double *qv, const double *gamma0,
+                                                  const double *u, const double *dsafe, const double *dsafe_obst,
+                                                  const double *obst, double *obj, double *maxv, double *sumv,
+                                                  int32_t *feasible, double *ci, double *cio)
+{
+    extern __shared__ double sh[];
+    Cta cta = {(int)blockDim.x};
+    const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp;
+    double *pos = sh, *red = sh + (size_t)n * 2;
+    for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+        ScpEval ev;
+        scp_evaluate(cta, nVeh, Hp, nObst, g + (size_t)b * n * 2, cterm + (size_t)b * n * 2, H + (size_t)b * n * Hp,
+                     qv + (size_t)b * n, gamma0[b], u + (size_t)b * n, dsafe + (size_t)b * nVeh * nVeh,
+                     nObst ? dsafe_obst + (size_t)b * nVeh * nObst : 0, nObst ? obst + (size_t)b * nObst * Hp * 2 : 0,
+                     p.dsafeExtra, p.constraint_tol, p.obstacle_eval_mode, pos, red, &ev,
+                     ci ? ci + (size_t)b * nVeh * nVeh * Hp : 0, cio ? cio + (size_t)b * nVeh * nObst * Hp : 0);
+        if (threadIdx.x == 0) {
+            obj[b] = ev.obj;
+            maxv[b] = ev.max_violation;
+            sumv[b] = ev.sum_violations;
+            feasible[b] = ev.feasible;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_forward(scpb200_dims d, const double *g, const double *cterm, const double *u,
+                                                 double *traj, double *U)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp, n = nVeh * Hp;
+    const size_t tot = (size_t)d.B * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n), c = (int)(e - (size_t)b * n), v = c / Hp, k = c - v * Hp;
+        const double *gv = g + ((size_t)b * n + v * Hp) * 2, *uv = u + (size_t)b * n + v * Hp;
+        double px = cterm[e * 2], py = cterm[e * 2 + 1];
+        for (int a = 0; a <= k; ++a) {
+            px += gv[(k - a) * 2] * uv[a];
+            py += gv[(k - a) * 2 + 1] * uv[a];
+        }
+        traj[(((size_t)b * Hp + k) * 2 + 0) * nVeh + v] = px;
+        traj[(((size_t)b * Hp + k) * 2 + 1) * nVeh + v] = py;
+        if (U) U[((size_t)b * Hp + k) * nVeh + v] = uv[k];
+    }
+}
+
+// Persistent CTAs pull instance indices from a global counter (SCP/IPM iteration counts vary per instance).
+__device__ __forceinline__ int next_instance(int *counter, int *slot)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) *slot = atomicAdd(counter, 1);
+    __syncthreads();
+    return *slot;
+}
+
+template <bool S_SHARED>
+__global__ void k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, int *counter, double *Sws, size_t S_stride)
+{
+    extern __shared__ double sh[];
+    __shared__ int slot;
+    Cta cta = {(int)blockDim.x};
+    ScpBump bp = {sh, 0};
+    ScpMem s;
+    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, S_SHARED ? (double *)0 : Sws + (size_t)blockIdx.x * S_stride, S_SHARED);
+    for (int b = next_instance(counter, &slot); b < d.B; b = next_instance(counter, &slot))
+        scp_solve_instance(cta, d, p, b, io, s);
+}
+
+template <bool S_SHARED>
+__global__ void k_qp_dense(int B, scpb200_params p, int n1, int mc, QpIO io, int *counter, double *Sws, size_t S_stride)
+{
+    extern __shared__ double sh[];
+    __shared__ int slot;
+    Cta cta = {(int)blockDim.x};
+    ScpBump bp = {sh, 0};
+    IpmMem m;
+    ipm_carve(bp, m, n1, mc, S_SHARED ? (double *)0 : Sws + (size_t)blockIdx.x * S_stride, S_SHARED);
+    for (int b = next_instance(counter, &slot); b < B; b = next_instance(counter, &slot))
+        qp_solve_instance(cta, p, n1, mc, b, io, m);
+}
+
+// ------------------------------------------------------------------------------------------------ launch planning
+struct SolvePlan {
+    int threads, grid, S_shared;
+    size_t smem_bytes, S_stride;    // S_stride in doubles (0 when S is in shared memory)
+    size_t ws_bytes;
+};
+
+#define WS_HEADER 256
+
+template <class KS, class KG>
+static int plan_common(KS kshared, KG kglobal, size_t sh_with_S, size_t sh_without_S, size_t S_doubles, int B,
+                       SolvePlan *pl)
+{
+    DevInfo di;
+    int rc = dev_info(&di);
+    if (rc) return rc;
+    pl->threads = env_int("SCPB200_THREADS", 256);
+    if (pl->threads % 32 || pl->threads < 32 || pl->threads > 1024) return set_err(SCPB200_ERR_ARG, "SCPB200_THREADS must be a multiple of 32 in [32,1024]");
+    const size_t lim = (size_t)di.smem_optin;
+    int occ = 0;
+    if (sh_with_S * 8 <= lim && !env_int("SCPB200_FORCE_GLOBAL_S", 0)) {
+        pl->S_shared = 1;
+        pl->smem_bytes = sh_with_S * 8;
+        pl->S_stride = 0;
+        CUDA_TRY(cudaFuncSetAttribute(kshared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kshared, pl->threads, pl->smem_bytes));
+    } else if (sh_without_S * 8 <= lim) {
+        pl->S_shared = 0;
+        pl->smem_bytes = sh_without_S * 8;
+        pl->S_stride = S_doubles;
+        CUDA_TRY(cudaFuncSetAttribute(kglobal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kglobal, pl->threads, pl->smem_bytes));
+    } else {
+        return set_err(SCPB200_ERR_SIZE, "problem too large: the per-instance vectors exceed shared memory");
+    }
+    if (occ < 1) return set_err(SCPB200_ERR_SIZE, "kernel cannot be resident (occupancy 0)");
+    const int cap = env_int("SCPB200_CTAS_PER_SM", 0);
+    if (cap > 0 && occ > cap) occ = cap;
+    long grid = (long)di.sms * occ;
+    if (grid > B) grid = B;
+    if (grid < 1) grid = 1;
+    pl->grid = (int)grid;
+    pl->ws_bytes = WS_HEADER + (pl->S_shared ? 0 : (size_t)di.sms * occ * S_doubles * 8);
+    return 0;
+}
+
+static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
+{
+    const int n1 = d->nVeh * d->Hp + 1;
+    return plan_common(k_scp_solve<true>, k_scp_solve<false>, scp_shared_doubles(d->nVeh, d->Hp, d->nObst, true),
+                       scp_shared_doubles(d->nVeh, d->Hp, d->nObst, false), ipm_S_doubles(n1), d->B, pl);
+}
+
+static int plan_qp(int n1, int mc, int B, SolvePlan *pl)
+{
+    return plan_common(k_qp_dense<true>, k_qp_dense<false>, ipm_shared_doubles(n1, mc, true),
+                       ipm_shared_doubles(n1, mc, false), ipm_S_doubles(n1), B, pl);
+}
+
+extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!bytes) return set_err(SCPB200_ERR_ARG, "bytes is NULL");
+    SolvePlan a, b;
+    scpb200_dims dd = *d;
+    if (dd.B < 1) dd.B = 1;
+    dd.B = 1 << 30;                                   // size for a full grid regardless of B
+    rc = plan_scp(&dd, &a);
+    if (rc) return rc;
+    const int n1 = d->nVeh * d->Hp + 1, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
+    rc = plan_qp(n1, mc, 1 << 30, &b);
+    if (rc) return rc;
+    *bytes = a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes;
+    return 0;
+}
+
+extern "C" int scpb200_qp_workspace_bytes(int32_t n1, int32_t mc, size_t *bytes)
+{
+    if (n1 < 1 || mc < 0 || !bytes) return set_err(SCPB200_ERR_ARG, "bad arguments");
+    SolvePlan b;
+    int rc = plan_qp(n1, mc, 1 << 30, &b);
+    if (rc) return rc;
+    *bytes = b.ws_bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ entry points
+extern "C" int scpb200_mpc_setup(const scpb200_dims *d, const scpb200_params *p, const double *x0, const double *u0,
+                                 const double *veh, const double *poly, double *ref, double *g, double *cterm,
+                                 double *H, double *qv, double *gamma0, double *abe, int32_t *setup_status,
+                                 void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !x0 || !u0 || !veh || !poly || !ref || !g || !cterm || !H || !qv || !gamma0)
+        return set_err(SCPB200_ERR_ARG, "scpb200_mpc_setup: NULL argument");
+    if (d->B == 0) return 0;
+    DevInfo di;
+    rc = dev_info(&di);
+    if (rc) return rc;
+    const int threads = 64;
+    const int grid = d->B < di.sms * 16 ? d->B : di.sms * 16;
+    k_mpc_setup<<<grid, threads, 0, (cudaStream_t)stream>>>(*d, *p, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe,
+                                                            setup_status);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_assemble_dense(const scpb200_dims *d, const scpb200_params *p, const double *g,
+                                      const double *cterm, const double *H, const double *qv, const double *ubar,
+                                      const double *dsafe, const double *dsafe_obst, const double *obst, double *P,
+                                      double *q, double *A, double *b, double *lb, double *ub, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !g || !cterm || !H || !qv || !ubar || !dsafe || !P || !q || !A || !b || !lb || !ub)
+        return set_err(SCPB200_ERR_ARG, "scpb200_assemble_dense: NULL argument");
+    if (d->nObst && (!dsafe_obst || !obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
+    if (d->B == 0) return 0;
+    DevInfo di;
+    rc = dev_info(&di);
+    if (rc) return rc;
+    const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
+    const size_t smem = ((size_t)n * 2 + (size_t)mc * 2 + mc + (size_t)n * 2 + n + 16) * 8;
+    if (smem > (size_t)di.smem_optin) return set_err(SCPB200_ERR_SIZE, "assemble: row data exceed shared memory");
+    CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble, 256, smem));
+    if (occ < 1) occ = 1;
+    long grid = (long)di.sms * occ;
+    if (grid > d->B) grid = d->B;
+    k_assemble<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(*d, *p, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q,
+                                                               A, b, lb, ub);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_qcqp_evaluate(const scpb200_dims *d, const scpb200_params *p, const double *g,
+                                     const double *cterm, const double *H, const double *qv, const double *gamma0,
+                                     const double *u, const double *dsafe, const double *dsafe_obst,
+                                     const double *obst, double *obj, double *max_violation, double *sum_violations,
+                                     int32_t *feasible, double *ci, double *ci_obst, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !g || !cterm || !H || !qv || !gamma0 || !u || !dsafe || !obj || !max_violation || !sum_violations || !feasible)
+        return set_err(SCPB200_ERR_ARG, "scpb200_qcqp_evaluate: NULL argument");
+    if (d->nObst && (!dsafe_obst || !obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
+    if (d->B == 0) return 0;
+    DevInfo di;
+    rc = dev_info(&di);
+    if (rc) return rc;
+    const size_t smem = ((size_t)d->nVeh * d->Hp * 2 + 8 * SCP_MAX_WARPS) * 8;
+    if (smem > (size_t)di.smem_optin) return set_err(SCPB200_ERR_SIZE, "evaluate: positions exceed shared memory");
+    CUDA_TRY(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = d->B < di.sms * 8 ? d->B : di.sms * 8;
+    k_evaluate<<<grid, 128, smem, (cudaStream_t)stream>>>(*d, *p, g, cterm, H, qv, gamma0, u, dsafe, dsafe_obst, obst, obj,
+                                                          max_violation, sum_violations, feasible, ci, ci_obst);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_forward_u(const scpb200_dims *d, const double *g, const double *cterm, const double *u,
+                                 double *traj, double *U, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!g || !cterm || !u || !traj) return set_err(SCPB200_ERR_ARG, "scpb200_forward_u: NULL argument");
+    if (d->B == 0) return 0;
+    const size_t tot = (size_t)d->B * d->nVeh * d->Hp;
+    const int grid = (int)((tot + 127) / 128 < 65535 ? (tot + 127) / 128 : 65535);
+    k_forward<<<grid, 128, 0, (cudaStream_t)stream>>>(*d, g, cterm, u, traj, U);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_qp_solve_dense(const scpb200_dims *d, const scpb200_params *p, int32_t n1, int32_t mc,
+                                      const double *P, const double *q, const double *A, const double *b,
+                                      const double *lb, const double *ub, double *x, double *fval, int32_t *iters,
+                                      int32_t *status, double *zA, void *ws, void *stream)
+{
+    if (!d || !p || n1 < 1 || mc < 0 || d->B < 0) return set_err(SCPB200_ERR_ARG, "scpb200_qp_solve_dense: bad dims");
+    if (!P || !q || (mc && (!A || !b)) || !lb || !ub || !x || !fval || !ws)
+        return set_err(SCPB200_ERR_ARG, "scpb200_qp_solve_dense: NULL argument");
+    if (d->B == 0) return 0;
+    SolvePlan pl;
+    int rc = plan_qp(n1, mc, d->B, &pl);
+    if (rc) return rc;
+    QpIO io = {P, q, A, b, lb, ub, x, fval, zA, iters, status};
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
+    int *counter = (int *)ws;
+    double *Sws = (double *)((char *)ws + WS_HEADER);
+    if (pl.S_shared)
+        k_qp_dense<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, Sws, pl.S_stride);
+    else
+        k_qp_dense<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, Sws, pl.S_stride);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                                 const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                                 const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                                 double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                                 double *max_violation, void *ws, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !g || !cterm || !H || !qv || !gamma0 || !dsafe || !u_inout || !ws)
+        return set_err(SCPB200_ERR_ARG, "scpb200_scp_solve: NULL argument");
+    if (d->nObst && (!dsafe_obst || !obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
+    if (p->max_scp_iter < 1) return set_err(SCPB200_ERR_ARG, "max_scp_iter must be >= 1");
+    if (d->B == 0) return 0;
+    SolvePlan pl;
+    rc = plan_scp(d, &pl);
+    if (rc) return rc;
+    ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
+                scp_iters, ipm_iters, status};
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
+    int *counter = (int *)ws;
+    double *Sws = (double *)((char *)ws + WS_HEADER);
+    if (pl.S_shared)
+        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, Sws, pl.S_stride);
+    else
+        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, Sws, pl.S_stride);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// launch geometry the solver would use for these dims (diagnostics for bench.py / DESIGN.md):
+// out[0]=grid, out[1]=threads, out[2]=dynamic shared bytes, out[3]=S in shared (1/0), out[4]=SM count
+extern "C" int scpb200_scp_plan(const scpb200_dims *d, int64_t *out)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    SolvePlan pl;
+    rc = plan_scp(d, &pl);
+    if (rc) return rc;
+    DevInfo di;
+    rc = dev_info(&di);
+    if (rc) return rc;
+    out[0] = pl.grid; out[1] = pl.threads; out[2] = (int64_t)pl.smem_bytes; out[3] = pl.S_shared; out[4] = di.sms;
+    return 0;
+}

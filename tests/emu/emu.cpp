@@ -1,0 +1,125 @@
+// tests/emu/emu.cpp — kernel-logic emulator.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the SAME device source the CUDA library is built from (csrc/*.cuh) with g++: a CTA becomes a loop
+// over thread ids per phase (ascending or descending — differing results expose intra-phase races), shared
+// memory becomes a heap buffer.  It lets the CPU test-suite (-m "not gpu") exercise the indexing, phase
+// structure and numerics of the kernels before they are run on a B200.  It is built into tests/emu/ by the
+// tests themselves, is never installed, and nothing in the product package can load it: the product's only
+// compute path is libscpb200.so on a CUDA device.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../senquential-convex-programming-for-trajectory-planning_b200/csrc/scp_kernels.cuh"
+
+static int g_nt = 128, g_reverse = 0, g_force_global_S = 0;
+
+extern "C" void emu_config(int nt, int reverse, int force_global_S)
+{
+    g_nt = nt;
+    g_reverse = reverse;
+    g_force_global_S = force_global_S;
+}
+
+static Cta *new_cta()
+{
+    Cta *c = (Cta *)calloc(1, sizeof(Cta));
+    c->nt = g_nt;
+    c->reverse = g_reverse;
+    return c;
+}
+
+extern "C" int emu_mpc_setup(const scpb200_dims *d, const scpb200_params *p, const double *x0, const double *u0,
+                             const double *veh, const double *poly, double *ref, double *g, double *cterm, double *H,
+                             double *qv, double *gamma0, double *abe, int32_t *setup_status)
+{
+    Cta *cta = new_cta();
+    std::vector<double> red(8 * SCP_MAX_WARPS);
+    int flag = 0;
+    for (int b = 0; b < d->B; ++b)
+        scp_setup_instance(*cta, *d, *p, b, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe, setup_status,
+                           red.data(), &flag);
+    free(cta);
+    return 0;
+}
+
+extern "C" int emu_assemble_dense(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                                  const double *H, const double *qv, const double *ubar, const double *dsafe,
+                                  const double *dsafe_obst, const double *obst, double *P, double *q, double *A,
+                                  double *b, double *lb, double *ub)
+{
+    Cta *cta = new_cta();
+    const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
+    std::vector<double> sh((size_t)n * 5 + (size_t)mc * 3 + 16);
+    for (int bi = 0; bi < d->B; ++bi)
+        scp_assemble_instance(*cta, *d, *p, bi, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, b, lb, ub,
+                              sh.data());
+    free(cta);
+    return 0;
+}
+
+extern "C" int emu_qcqp_evaluate(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                                 const double *H, const double *qv, const double *gamma0, const double *u,
+                                 const double *dsafe, const double *dsafe_obst, const double *obst, double *obj,
+                                 double *max_violation, double *sum_violations, int32_t *feasible, double *ci,
+                                 double *ci_obst)
+{
+    Cta *cta = new_cta();
+    const int nVeh = d->nVeh, Hp = d->Hp, nObst = d->nObst, n = nVeh * Hp;
+    std::vector<double> pos((size_t)n * 2), red(8 * SCP_MAX_WARPS);
+    for (int b = 0; b < d->B; ++b) {
+        ScpEval ev;
+        scp_evaluate(*cta, nVeh, Hp, nObst, g + (size_t)b * n * 2, cterm + (size_t)b * n * 2, H + (size_t)b * n * Hp,
+                     qv + (size_t)b * n, gamma0[b], u + (size_t)b * n, dsafe + (size_t)b * nVeh * nVeh,
+                     nObst ? dsafe_obst + (size_t)b * nVeh * nObst : 0, nObst ? obst + (size_t)b * nObst * Hp * 2 : 0,
+                     p->dsafeExtra, p->constraint_tol, p->obstacle_eval_mode, pos.data(), red.data(), &ev,
+                     ci ? ci + (size_t)b * nVeh * nVeh * Hp : 0, ci_obst ? ci_obst + (size_t)b * nVeh * nObst * Hp : 0);
+        obj[b] = ev.obj;
+        max_violation[b] = ev.max_violation;
+        sum_violations[b] = ev.sum_violations;
+        feasible[b] = ev.feasible;
+    }
+    free(cta);
+    return 0;
+}
+
+extern "C" int emu_qp_solve_dense(const scpb200_dims *d, const scpb200_params *p, int32_t n1, int32_t mc,
+                                  const double *P, const double *q, const double *A, const double *b, const double *lb,
+                                  const double *ub, double *x, double *fval, int32_t *iters, int32_t *status, double *zA)
+{
+    Cta *cta = new_cta();
+    const bool sh = !g_force_global_S;
+    std::vector<double> smem(ipm_shared_doubles(n1, mc, sh)), Sg(ipm_S_doubles(n1));
+    ScpBump bp = {smem.data(), 0};
+    IpmMem m;
+    ipm_carve(bp, m, n1, mc, Sg.data(), sh);
+    QpIO io = {P, q, A, b, lb, ub, x, fval, zA, iters, status};
+    for (int bi = 0; bi < d->B; ++bi) qp_solve_instance(*cta, *p, n1, mc, bi, io, m);
+    free(cta);
+    return 0;
+}
+
+extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                             const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                             const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                             double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                             double *max_violation)
+{
+    Cta *cta = new_cta();
+    const bool sh = !g_force_global_S;
+    std::vector<double> smem(scp_shared_doubles(d->nVeh, d->Hp, d->nObst, sh)), Sg(ipm_S_doubles(d->nVeh * d->Hp + 1));
+    ScpBump bp = {smem.data(), 0};
+    ScpMem s;
+    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, Sg.data(), sh);
+    ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
+                scp_iters, ipm_iters, status};
+    for (int b = 0; b < d->B; ++b) scp_solve_instance(*cta, *d, *p, b, io, s);
+    free(cta);
+    return 0;
+}
+
+extern "C" size_t emu_scp_shared_bytes(int nVeh, int Hp, int nObst, int S_in_shared)
+{
+    return scp_shared_doubles(nVeh, Hp, nObst, S_in_shared != 0) * 8;
+}

@@ -1,0 +1,130 @@
+"""Python front-end of the kernel-logic emulator (tests/emu/emu.cpp).  TEST INFRASTRUCTURE ONLY — see emu.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+PKG = "senquential-convex-programming-for-trajectory-planning_b200"
+SRC = os.path.join(HERE, "emu.cpp")
+LIB = os.path.join(HERE, "libscpb200_emu.so")
+CSRC = os.path.join(ROOT, PKG, "csrc")
+
+capi = importlib.import_module(PKG + "._capi")
+Dims, Params = capi.Dims, capi.Params
+_lib = None
+DBL = C.POINTER(C.c_double)
+I32 = C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    newest = max(os.path.getmtime(d) for d in deps)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB, SRC],
+                       check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.emu_scp_shared_bytes.restype = C.c_size_t
+    return _lib
+
+
+def config(nt=128, reverse=False, force_global_S=False):
+    lib().emu_config(C.c_int(nt), C.c_int(int(reverse)), C.c_int(int(force_global_S)))
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(DBL)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(I32)
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def mpc_setup(x0, u0, veh, poly, Hp, params):
+    x0, u0, veh, poly = _c(x0), _c(u0), _c(veh), _c(poly)
+    B, nVeh, nPts = x0.shape[0], x0.shape[1], poly.shape[2]
+    d = Dims(B, nVeh, Hp, 0, nPts)
+    out = dict(ref=np.zeros((B, nVeh, Hp, 2)), g=np.zeros((B, nVeh, Hp, 2)), cterm=np.zeros((B, nVeh, Hp, 2)),
+               H=np.zeros((B, nVeh, Hp, Hp)), qv=np.zeros((B, nVeh, Hp)), gamma0=np.zeros(B),
+               abe=np.zeros((B, nVeh, 48)), setup_status=np.zeros(B, dtype=np.int32))
+    lib().emu_mpc_setup(C.byref(d), C.byref(params), _d(x0), _d(u0), _d(veh), _d(poly), _d(out["ref"]), _d(out["g"]),
+                        _d(out["cterm"]), _d(out["H"]), _d(out["qv"]), _d(out["gamma0"]), _d(out["abe"]),
+                        _i(out["setup_status"]))
+    return out
+
+
+def _obst(dsafe_obst, obst):
+    if obst is None:
+        return 0, None, None
+    obst = _c(obst)
+    return obst.shape[1], _c(dsafe_obst), obst
+
+
+def assemble_dense(g, cterm, H, qv, ubar, dsafe, params, dsafe_obst=None, obst=None):
+    g, cterm, H, qv, ubar, dsafe = _c(g), _c(cterm), _c(H), _c(qv), _c(ubar), _c(dsafe)
+    B, nVeh, Hp = g.shape[0], g.shape[1], g.shape[2]
+    nObst, dso, ob = _obst(dsafe_obst, obst)
+    d = Dims(B, nVeh, Hp, nObst, 2)
+    n1 = nVeh * Hp + 1
+    mc = Hp * (nVeh * (nVeh - 1) // 2 + nVeh * nObst)
+    P, q, A, b = np.full((B, n1, n1), np.nan), np.full((B, n1), np.nan), np.full((B, mc, n1), np.nan), np.full((B, mc), np.nan)
+    lb, ub = np.full((B, n1), np.nan), np.full((B, n1), np.nan)
+    lib().emu_assemble_dense(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(ubar), _d(dsafe), _d(dso),
+                             _d(ob), _d(P), _d(q), _d(A), _d(b), _d(lb), _d(ub))
+    return P, q, A, b, lb, ub
+
+
+def qcqp_evaluate(g, cterm, H, qv, gamma0, u, dsafe, params, dsafe_obst=None, obst=None):
+    g, cterm, H, qv, gamma0, u, dsafe = _c(g), _c(cterm), _c(H), _c(qv), _c(gamma0), _c(u), _c(dsafe)
+    B, nVeh, Hp = g.shape[0], g.shape[1], g.shape[2]
+    nObst, dso, ob = _obst(dsafe_obst, obst)
+    d = Dims(B, nVeh, Hp, nObst, 2)
+    obj, mv, sv, feas = np.zeros(B), np.zeros(B), np.zeros(B), np.zeros(B, dtype=np.int32)
+    ci = np.zeros((B, nVeh, nVeh, Hp))
+    cio = np.zeros((B, nVeh, max(nObst, 1), Hp))
+    lib().emu_qcqp_evaluate(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(gamma0), _d(u), _d(dsafe),
+                            _d(dso), _d(ob), _d(obj), _d(mv), _d(sv), _i(feas), _d(ci), _d(cio) if nObst else None)
+    return dict(obj=obj, max_violation=mv, sum_violations=sv, feasible=feas.astype(bool), ci=ci, ci_obst=cio[:, :, :nObst])
+
+
+def qp_solve_dense(P, q, A, b, lb, ub, params):
+    P, q, A, b, lb, ub = _c(P), _c(q), _c(A), _c(b), _c(lb), _c(ub)
+    B, n1, mc = P.shape[0], P.shape[1], A.shape[1]
+    d = Dims(B, 1, 1, 0, 2)
+    x, fval = np.zeros((B, n1)), np.zeros(B)
+    iters, status, zA = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros((B, mc))
+    lib().emu_qp_solve_dense(C.byref(d), C.byref(params), C.c_int32(n1), C.c_int32(mc), _d(P), _d(q), _d(A), _d(b), _d(lb),
+                             _d(ub), _d(x), _d(fval), _i(iters), _i(status), _d(zA))
+    return dict(x=x, fval=fval, iters=iters, status=status, zA=zA)
+
+
+def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=None):
+    g, cterm, H, qv, gamma0, dsafe = _c(g), _c(cterm), _c(H), _c(qv), _c(gamma0), _c(dsafe)
+    B, nVeh, Hp = g.shape[0], g.shape[1], g.shape[2]
+    nObst, dso, ob = _obst(dsafe_obst, obst)
+    d = Dims(B, nVeh, Hp, nObst, 2)
+    n = nVeh * Hp
+    u = _c(u).reshape(B, n).copy()
+    traj, U = np.zeros((B, Hp, 2, nVeh)), np.zeros((B, Hp, nVeh))
+    log = np.zeros((B, params.max_scp_iter, capi.LOG_W))
+    si, ii, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    obj, mv = np.zeros(B), np.zeros(B)
+    lib().emu_scp_solve(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(gamma0), _d(dsafe), _d(dso), _d(ob),
+                        _d(u), _d(traj), _d(U), _d(log), _i(si), _i(ii), _i(st), _d(obj), _d(mv))
+    return dict(u=u, traj=traj, U=U, log=log, scp_iters=si, ipm_iters=ii, status=st, obj=obj, max_violation=mv)

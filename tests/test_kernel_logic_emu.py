@@ -1,0 +1,193 @@
+"""CPU tests of the CUDA kernels' LOGIC: the device source (csrc/*.cuh) compiled with g++ by tests/emu and run
+phase by phase on the host, checked against the oracle and the reference's golden vectors.  The parity tests
+proper run the real kernels on a B200 (tests/test_gpu_parity.py, -m gpu)."""
+import glob
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_setup_inputs, load_golden
+from emu import emu
+
+capi = importlib.import_module("senquential-convex-programming-for-trajectory-planning_b200._capi")
+STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+FAST_FILES = [f for f in STEP_FILES if "hp50" not in f and "hp20" not in f]
+
+
+def params_for(G, **kw):
+    p = capi.default_params_py()
+    p.dt, p.uLim, p.dsafeExtra = float(G["sc_dt"]), float(G["sc_uLim"]), float(G["sc_dsafeExtra"])
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.fixture(autouse=True)
+def _reset_emu():
+    emu.config(nt=128, reverse=False)
+    yield
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+@pytest.mark.parametrize("reverse", [False, True])
+def test_setup_kernel_vs_oracle_and_golden(oracle, fname, reverse):
+    G = load_golden(fname)
+    Hp = int(G["sc_Hp"])
+    emu.config(nt=64, reverse=reverse)
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    E = emu.mpc_setup(x0, u0, veh, poly, Hp, params_for(G))
+    O = oracle.mpc_setup(x0, u0, veh, poly, Hp=Hp, dt=float(G["sc_dt"]))
+    assert (E["setup_status"] == 0).all()
+    for k in ["ref", "g", "cterm", "H", "abe"]:
+        scale = np.abs(O[k]).max()
+        assert np.abs(E[k] - O[k]).max() <= 1e-12 * scale, k
+    assert np.abs(E["qv"] - O["qv"]).max() <= 1e-12 * np.abs(O["g"]).max() * np.abs(O["ref"]).max() * 2 * 20 * Hp
+    assert abs(E["gamma0"][0] - O["gamma0"][0]) <= 1e-12 * max(1.0, abs(O["gamma0"][0])) * Hp
+    # and straight against the reference's own arrays
+    nVeh = int(G["sc_nVeh"])
+    for v in range(nVeh):
+        assert np.abs(E["H"][0, v] - G["Phi_0"][:, :, v]).max() <= 1e-12 * np.abs(G["Phi_0"]).max()
+        assert np.abs(E["cterm"][0, v].ravel() - G["const_term"][:, v]).max() <= 1e-12 * np.abs(G["const_term"]).max()
+
+
+def test_setup_kernel_noise_matches_oracle(oracle):
+    G = load_golden("circle8_hp10_step10.npz")
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    B = 3
+    x0, u0, veh, poly = (np.repeat(a, B, axis=0) for a in (x0, u0, veh, poly))
+    p = params_for(G, noise_sigma=3e-6, seed=12345, instance0=7, noise_counter=3)
+    E = emu.mpc_setup(x0, u0, veh, poly, 10, p)
+    O = oracle.mpc_setup(x0, u0, veh, poly, Hp=10, dt=0.4, noise_sigma=3e-6, seed=12345, instance0=7, noise_counter=3)
+    assert np.abs(E["cterm"] - O["cterm"]).max() <= 1e-12 * np.abs(O["cterm"]).max()
+    assert np.abs(E["abe"] - O["abe"]).max() <= 1e-12 * np.abs(O["abe"]).max()
+    assert np.abs(E["cterm"][0] - E["cterm"][1]).max() > 1e-9          # instances draw different noise
+    N = oracle.mpc_setup(x0, u0, veh, poly, Hp=10, dt=0.4)
+    assert 1e-9 < np.abs(E["cterm"] - N["cterm"]).max() < 1e-3          # and it is small
+
+
+def _setup(oracle, G):
+    out = oracle.mpc_setup(*golden_setup_inputs(G), Hp=int(G["sc_Hp"]), dt=float(G["sc_dt"]))
+    return out
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+@pytest.mark.parametrize("reverse", [False, True])
+def test_assemble_kernel_vs_reference(oracle, fname, reverse):
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    emu.config(nt=256, reverse=reverse)
+    its = sorted(int(k.split("_")[1]) for k in G if k.startswith("Aineq_"))
+    for it in its:
+        P, q, A, b, lb, ub = emu.assemble_dense(S["g"], S["cterm"], S["H"], S["qv"], G["prev_u"][it][None],
+                                                G["sc_dsafeVehicles"][None], params_for(G))
+        assert not np.isnan(P).any() and not np.isnan(A).any() and not np.isnan(b).any()
+        assert np.abs(P[0] - G[f"P_{it}"]).max() <= 1e-12 * np.abs(G[f"P_{it}"]).max()
+        assert np.abs(A[0] - G[f"Aineq_{it}"]).max() <= 1e-11 * np.abs(G[f"Aineq_{it}"]).max()
+        assert (A[0][G[f"Aineq_{it}"] == 0] == 0).all()
+        assert np.abs(b[0] - G[f"bineq_{it}"]).max() <= 1e-11 * np.abs(G[f"bineq_{it}"]).max()
+        qscale = 2 * 20 * int(G["sc_Hp"]) * np.abs(S["g"]).max() * np.abs(S["ref"]).max()   # terms summed in Psi_0
+        assert np.abs(q[0] - G[f"q_{it}"]).max() <= 1e-13 * qscale
+        np.testing.assert_array_equal(lb[0], G[f"lb_{it}"])
+        np.testing.assert_array_equal(ub[0], G[f"ub_{it}"])
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_evaluate_kernel_vs_reference(oracle, fname):
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    ev = emu.qcqp_evaluate(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["u_final"][None],
+                           G["sc_dsafeVehicles"][None], params_for(G))
+    assert bool(ev["feasible"][0]) == bool(G["eval_feasible"])
+    assert abs(ev["obj"][0] - float(G["eval_obj"])) <= 1e-9 * max(1.0, abs(float(G["eval_obj"])))
+    assert abs(ev["max_violation"][0] - float(G["eval_max_violation"])) < 1e-9
+    assert abs(ev["sum_violations"][0] - float(G["eval_sum_violations"])) < 1e-9
+    fin = np.isfinite(G["eval_ci"])
+    assert (np.isfinite(ev["ci"][0]) == fin).all()
+    assert np.abs(ev["ci"][0][fin] - G["eval_ci"][fin]).max() < 1e-9
+
+
+def _qp_from_golden(oracle, G, S, it):
+    return oracle.assemble_dense(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], G["prev_u"][it], G["sc_dsafeVehicles"],
+                                 float(G["sc_dsafeExtra"]), float(G["sc_uLim"]))
+
+
+@pytest.mark.parametrize("fname", FAST_FILES)
+@pytest.mark.parametrize("reverse,force_global", [(False, False), (True, False), (False, True)])
+def test_dense_qp_kernel_vs_reference_solution(oracle, fname, reverse, force_global):
+    """K3 on the reference's dense QPs (every SCP iteration of the golden step): x within 1e-6 of the
+    extended-precision minimiser, objective within 1e-6 relative, constraints satisfied to 1e-6."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    emu.config(nt=128, reverse=reverse, force_global_S=force_global)
+    its = list(range(int(G["scp_iters"])))
+    if reverse or force_global:
+        its = its[:2]
+    qps = [_qp_from_golden(oracle, G, S, it) for it in its]
+    P, q, A, b, lb, ub = (np.stack([qp[k] for qp in qps]) for k in range(6))
+    r = emu.qp_solve_dense(P, q, A, b, lb, ub, params_for(G))
+    for j, it in enumerate(its):
+        xs = G["x"][it]
+        assert r["status"][j] == 0, (it, r["status"][j], r["iters"][j])
+        assert np.abs(r["x"][j] - xs).max() < 1e-6
+        f_ref = 0.5 * xs @ P[j] @ xs + q[j] @ xs
+        assert abs(r["fval"][j] - f_ref) <= 1e-6 * max(1.0, abs(f_ref))
+        viol = max((A[j] @ r["x"][j] - b[j]).max(), (lb[j] - r["x"][j]).max(), (r["x"][j][:-1] - ub[j][:-1]).max())
+        assert viol <= 1e-6
+
+
+@pytest.mark.parametrize("fname", FAST_FILES)
+def test_dense_and_structured_solvers_agree_with_oracle_iterations(oracle, fname):
+    """The kernel's interior-point iteration follows coneqp: same iteration count (+-1) as the oracle run in
+    double with the same tolerances and regularisation off where that converges."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    P, q, A, b, lb, ub = _qp_from_golden(oracle, G, S, 0)
+    p = params_for(G, qp_abstol=1e-8, qp_reltol=1e-8, qp_feastol=1e-8)
+    r = emu.qp_solve_dense(P[None], q[None], A[None], b[None], lb[None], ub[None], p)
+    o = oracle.qp_boxed(P, q, A, b, lb, ub, opts=dict(abstol=1e-8, reltol=1e-8, feastol=1e-8))
+    assert o["status"] == 0 and r["status"][0] == 0
+    assert abs(int(r["iters"][0]) - o["iterations"]) <= 1
+    assert np.abs(r["x"][0] - o["x"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("fname", FAST_FILES)
+@pytest.mark.parametrize("reverse", [False, True])
+def test_scp_kernel_teacher_forced(oracle, fname, reverse):
+    """K4 with max_scp_iter = 1 from the reference's own linearisation points: one QP per instance, batch =
+    the SCP iterations of the golden step.  u within 1e-6 (bar 1e-5), objective 1e-6, slack 1e-6."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    nit = int(G["scp_iters"])
+    emu.config(nt=128, reverse=reverse)
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    p = params_for(G, max_scp_iter=1)
+    r = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]),
+                      rep(G["sc_dsafeVehicles"][None]), G["prev_u"][:nit], p)
+    for it in range(nit):
+        assert np.abs(r["u"][it] - G["x"][it][:-1]).max() < 1e-6, it
+        assert abs(r["log"][it, 0, 0] - G["slack"][it]) < 1e-6
+        assert abs(r["log"][it, 0, 1] - G["SCP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][it]))
+        assert abs(r["log"][it, 0, 2] - G["QCQP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["QCQP_ObjVal"][it]))
+        assert bool(r["log"][it, 0, 5]) == bool(G["feasible"][it])
+        assert (r["status"][it] & (capi.ST_QP_MAXITER | capi.ST_QP_PIVOT)) == 0
+
+
+@pytest.mark.parametrize("fname", FAST_FILES)
+def test_scp_kernel_free_running(oracle, fname):
+    """K4 free-running from the reference's warm start: iteration count and converged u (where the SCP map is
+    stable; see test_oracle_golden.test_scp_loop_free_running), trajectories within 1e-4 m."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    r = emu.scp_solve(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], G["u_warm"][None],
+                      params_for(G))
+    assert bool(r["log"][0, r["scp_iters"][0] - 1, 5]) == bool(G["feasible"][-1])
+    if int(G["scp_iters"]) <= 5:
+        assert r["scp_iters"][0] == int(G["scp_iters"])
+        assert np.abs(r["u"][0] - G["u_final"]).max() < 1e-6
+        assert np.abs(r["traj"][0] - G["Traj"]).max() < 1e-4
+        assert np.abs(r["U"][0] - G["U"]).max() < 1e-6
+    else:
+        assert abs(int(r["scp_iters"][0]) - int(G["scp_iters"])) <= 2
+    assert (r["status"][0] & (capi.ST_SCP_MAXITER | capi.ST_INFEASIBLE)) == 0
