@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — batched SCP QP solves/s on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--hp HP]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the default 8-vehicle circle scenario (Hp = 10), 1024 perturbed instances per
+GPU with process noise (Monte-Carlo), synthetic inputs from scenarios.circle_batch.  A "step" is the
+controller stage of one closed-loop MPC step over the whole batch: K1 set-up -> K4 fused SCP solve (-> linear
+advance).  `value` = QPs solved (sum over instances of SCP iterations) per second, inputs resident in HBM, timed
+with CUDA events per step (L2 flushed between steps), max over ranks.  `e2e` = the same through the public API
+with HOST buffers (pinned H2D of every input, D2H of every result, per step).  `cpu_baseline` / `--impl
+reference` time the oracle port of the reference's CPU path on the box's host cores (bounded sample).
+
+The product arm never touches oracle/: only the cpu_baseline leg and `--impl reference` import it.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "senquential-convex-programming-for-trajectory-planning_b200"
+
+METRIC = "batched SCP QP solves/sec"
+UNIT = "QP/s"
+
+
+# ---------------------------------------------------------------------------------------------------- helpers
+def algorithmic_flops_per_ipm_iteration(nVeh, Hp):
+    """n1^3/3 (Cholesky) + 2 sum_rows nnz_r^2 (A'DA) + 8 n1^2 (two RHS) + 8 nnz(G) (mat-vecs)."""
+    n1 = nVeh * Hp + 1
+    npair = nVeh * (nVeh - 1) // 2
+    sum_nnz2 = npair * sum((2 * (k + 1) + 1) ** 2 for k in range(Hp))
+    nnzG = npair * sum(2 * (k + 1) + 1 for k in range(Hp)) + 2 * n1
+    return n1 ** 3 / 3.0 + 2.0 * sum_nnz2 + 8.0 * n1 ** 2 + 8.0 * nnzG
+
+
+def assembly_bytes_per_qp(nVeh, Hp):
+    """out = 8 (n1^2 + n1 + mc n1 + mc + 2 n1); in = 8 (16 nVeh + nVeh^2 + nVeh Hp)."""
+    n1 = nVeh * Hp + 1
+    mc = Hp * nVeh * (nVeh - 1) // 2
+    return 8 * (n1 * n1 + n1 + mc * n1 + mc + 2 * n1) + 8 * (16 * nVeh + nVeh * nVeh + nVeh * Hp)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rank_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def cpu_controller_run(B, nVeh, Hp, steps, warmup, instance0, threads, opts, noise_sigma, seed, uMax, duLim, step_lo, step_hi):
+    """The oracle port of the reference's CPU path on the same closed-loop workload: per MPC step
+    MPCclass set-up (orc_mpc_setup) + SCP_controller (orc_scp_controller_batch, dense assembly + coneqp), advance
+    on the linear model.  Returns (QPs solved in the timed steps, seconds, ipm iterations)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle  # noqa: E402  (cpu_baseline / --impl reference only)
+    scen = importlib.import_module(PKG + ".scenarios")
+    cb = scen.circle_batch(B, nVeh=nVeh, Hp=Hp, instance0=instance0, step_lo=step_lo, step_hi=step_hi)
+    x0, u0, u = cb.x0.copy(), cb.u0.copy(), np.zeros((B, nVeh * Hp))
+    qps = ipm = 0
+    t_total = 0.0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        S = oracle.mpc_setup(x0, u0, cb.veh, cb.poly, Hp=Hp, dt=scen.DT, noise_sigma=noise_sigma, seed=seed,
+                             instance0=instance0, noise_counter=s)
+        R = oracle.scp_controller_batch(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], cb.dsafe, u, opts=opts, threads=threads)
+        dt_ = time.perf_counter() - t0
+        u = R["u"]
+        ua = np.clip(R["U"][:, 0, :], -uMax, uMax)
+        ua = np.clip(ua, u0 - duLim, u0 + duLim)
+        abe = S["abe"]
+        Ad, Bd, Ed = abe[..., :36].reshape(B, nVeh, 6, 6), abe[..., 36:42], abe[..., 42:48]
+        x0 = np.einsum("bvij,bvj->bvi", Ad, x0) + Bd * ua[..., None] + Ed
+        u0 = ua
+        if s >= warmup:
+            qps += int(R["scp_iters"].sum()); ipm += int(R["ipm_iters"].sum()); t_total += dt_
+    return qps, t_total, ipm
+
+
+def run_reference(args):
+    rank, _, world = rank_env()
+    if rank != 0:
+        return
+    scen = importlib.import_module(PKG + ".scenarios")
+    cores = os.cpu_count() or 1
+    Bs = args.cpu_sample
+    opts = dict(abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100)        # CVXOPT's documented defaults
+    qps, sec, ipm = cpu_controller_run(Bs, args.nveh, args.hp, args.steps, args.warmup, 0, cores, opts, args.noise_sigma,
+                                       args.seed, scen.MECH_LIMIT, scen.DU_LIM, args.step_lo, args.step_hi)
+    val = qps / sec if sec > 0 else 0.0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, Bs, note="bounded sample of the product arm's workload on the host cores"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{Bs} instances x {args.steps} closed-loop MPC steps ({qps} QPs, {ipm} IPM iterations), "
+                                   f"oracle coneqp restatement at CVXOPT default tolerances, {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B_per_gpu, note=None):
+    cfg = {"workload": f"default 8-vehicle circle scenario (Scenarios.py:109-125), Hp={args.hp}, batched x{B_per_gpu} per GPU, "
+                       f"perturbed instances with process noise sigma={args.noise_sigma} (Monte-Carlo), closed-loop MPC steps "
+                       f"starting at step U{{{args.step_lo}..{args.step_hi}}} (BASELINE.json configs[1])",
+           "nVeh": args.nveh, "Hp": args.hp, "batch_per_gpu": B_per_gpu, "n1": args.nveh * args.hp + 1,
+           "mc": args.hp * args.nveh * (args.nveh - 1) // 2, "l2": "flushed between timed steps (256 MiB write)",
+           "qp_tolerances": {"abstol": 1e-10, "reltol": 1e-10, "feastol": 1e-9}}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = rank_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi = importlib.import_module(PKG + "._capi")
+    batch = importlib.import_module(PKG + ".batch")
+    scen = importlib.import_module(PKG + ".scenarios")
+    B, nVeh, Hp = args.batch, args.nveh, args.hp
+    inst0 = rank * B                                        # weak scaling: B instances per rank, disjoint global ids
+    cb = scen.circle_batch(B, nVeh=nVeh, Hp=Hp, instance0=inst0, step_lo=args.step_lo, step_hi=args.step_hi)
+    p = capi.Params()
+    capi.load().scpb200_default_params(C.byref(p))
+    p.noise_sigma, p.seed, p.instance0 = args.noise_sigma, args.seed, inst0
+    bs = batch.BatchSCP(B, nVeh, Hp, params=p, device=dev, keep_log=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    uMax, duLim = scen.MECH_LIMIT, scen.DU_LIM
+
+    def reset():
+        bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, nVeh * Hp)))
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step(s):
+        bs.params.noise_counter = s
+        bs.setup()
+        bs.solve()
+        bs.advance_linear(uMax, duLim)
+
+    # ---------------- device-resident timing (value) ----------------
+    reset()
+    for s in range(args.warmup):
+        device_step(s)
+    torch.cuda.synchronize(dev)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    evs0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    evs1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    qp_counts = torch.zeros(args.steps, dtype=torch.int64, device=dev)
+    ipm_counts = torch.zeros(args.steps, dtype=torch.int64, device=dev)
+    stat_counts = torch.zeros(5, dtype=torch.int64, device=dev)   # instances x steps with status bits 1,2,4,8,16
+    launches0 = bs.kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                       # L2 flush, outside the event pair
+        ev0[k].record()
+        bs.params.noise_counter = args.warmup + k
+        bs.setup()
+        evs0[k].record()
+        bs.solve()
+        evs1[k].record()
+        bs.advance_linear(uMax, duLim)
+        ev1[k].record()
+        qp_counts[k] = bs.scp_iters.sum()
+        ipm_counts[k] = bs.ipm_iters.sum()
+        stat_counts += torch.stack([((bs.status >> i) & 1).sum() for i in range(5)])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = bs.kernel_launches - launches0
+    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)])
+    solve_ms = np.array([evs0[k].elapsed_time(evs1[k]) for k in range(args.steps)])
+    t_dev = float(step_ms.sum()) * 1e-3
+    qps_rank = int(qp_counts.sum().item())
+    ipm_rank = int(ipm_counts.sum().item())
+    qp_per_step = qp_counts.cpu().numpy()
+    ipm_per_step = ipm_counts.cpu().numpy()
+
+    # ---------------- end-to-end through the public API with host buffers (e2e) ----------------
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).pin_memory()
+    h_in = {k: pin(getattr(cb, k)) for k in ("x0", "u0", "veh", "poly", "dsafe")}
+    h_in["u"] = pin(np.zeros((B, nVeh * Hp)))
+    h_out = {k: torch.empty_like(getattr(bs, k), device="cpu").pin_memory() for k in
+             ("U", "traj", "u", "scp_iters", "ipm_iters", "status", "obj", "max_violation", "x0", "u0")}
+    h2d = sum(t.numel() * t.element_size() for t in h_in.values())
+    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+
+    def e2e_step(s):
+        for k, t in h_in.items():                           # the caller's per-step inputs: measured state, scenario, warm start
+            getattr(bs, k).copy_(t, non_blocking=True)
+        bs.params.noise_counter = s
+        bs.setup()
+        bs.solve()
+        bs.advance_linear(uMax, duLim)
+        for k, t in h_out.items():
+            t.copy_(getattr(bs, k), non_blocking=True)
+        torch.cuda.synchronize(dev)
+        h_in["x0"].copy_(h_out["x0"]); h_in["u0"].copy_(h_out["u0"]); h_in["u"].copy_(h_out["u"])   # next step's host inputs
+        return int(h_out["scp_iters"].sum())
+
+    for s in range(args.warmup):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_qps = 0
+    for k in range(args.steps):
+        e2e_qps += e2e_step(args.warmup + k)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # ---------------- assembly kernel (K2) against the HBM roofline ----------------
+    asm = None
+    if rank == 0 and not args.skip_assembly:
+        outbuf = bs.assemble_dense()
+        torch.cuda.synchronize(dev)
+        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+        for i in range(3):
+            bs.assemble_dense_into(bs.u, outbuf)
+        for i in range(10):
+            flush.zero_()
+            a0[i].record(); bs.assemble_dense_into(bs.u, outbuf); a1[i].record()
+        torch.cuda.synchronize(dev)
+        ams = float(np.mean([a0[i].elapsed_time(a1[i]) for i in range(10)]))
+        peaks, how = measured_peaks()
+        abytes = assembly_bytes_per_qp(nVeh, Hp) * B
+        asm = {"bound": "hbm", "kernel": "k_assemble", "achieved": abytes / (ams * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+               "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+               "ms_per_launch": ams, "algorithmic_bytes_per_launch": abytes}
+        del outbuf
+
+    # ---------------- reduce over ranks ----------------
+    t_max, qps_all, e2e_max, e2e_all = t_dev, qps_rank, t_e2e, e2e_qps
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank], dtype=torch.int64, device=dev)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        t_max, e2e_max = float(tt[0]), float(tt[1])
+        qps_all, e2e_all, ipm_all = int(cc[0]), int(cc[1]), int(cc[2])
+        # the optional all-gather of trajectories / statistics, off the timed path
+        gathered = [torch.empty_like(bs.U) for _ in range(world)]
+        dist.all_gather(gathered, bs.U)
+    else:
+        ipm_all = ipm_rank
+
+    if rank == 0:
+        value = qps_all / t_max
+        fit = algorithmic_flops_per_ipm_iteration(nVeh, Hp)
+        # dominant kernel: k_scp_solve (FP64 pipe).  Flops per launch = F_it x (IPM iterations + 1 start-point
+        # factorisation per QP) of that launch; duration = CUDA events around the launch on its stream.
+        fl = fit * (ipm_per_step + qp_per_step)
+        ach = float(fl.sum() / (solve_ms.sum() * 1e-3) / 1e12)
+        fp64_peak = float(os.environ.get("SCPB200_FP64_PEAK_TFLOPS", "37.0"))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, B),
+            "e2e": {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak, "traffic": None,
+                         "peak_source": "nominal B200 FP64 (HGX datasheet 296 TF / 8 GPUs); not in MEASURED_PEAKS.json",
+                         "algorithmic_flops_per_ipm_iteration": fit, "solve_share_of_step": float(solve_ms.sum() / step_ms.sum())},
+            "roofline_assembly": asm,
+            "stats": {"qps_total": qps_all, "ipm_iterations_total": ipm_all, "qp_per_instance_step": qps_all / (world * B * args.steps),
+                      "ipm_per_qp": ipm_all / max(1, qps_all),
+                      "status_counts_rank0": dict(zip(["qp_maxiter", "qp_pivot", "scp_maxiter", "infeasible", "setup"],
+                                                      [int(v) for v in stat_counts.cpu()])),
+                      "wall_s_bracket": t_wall, "p50_ms_per_mpc_step": float(np.median(step_ms)),
+                      "plan": bs.plan()},
+        }
+        if not args.skip_cpu and world >= 1:
+            cores = os.cpu_count() or 1
+            opts = dict(abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100)
+            cq, cs, ci = cpu_controller_run(args.cpu_sample, nVeh, Hp, args.steps, 0, 0, cores, opts, args.noise_sigma, args.seed,
+                                            uMax, duLim, args.step_lo, args.step_hi)
+            line["cpu_baseline"] = {"value": cq / cs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} instances x {args.steps} closed-loop MPC steps ({cq} QPs), oracle "
+                                              f"coneqp restatement at CVXOPT default tolerances (1e-7/1e-6/1e-7), {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="instances per GPU")
+    ap.add_argument("--nveh", type=int, default=8)
+    ap.add_argument("--hp", type=int, default=10)
+    ap.add_argument("--noise-sigma", dest="noise_sigma", type=float, default=3e-6)
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--step-lo", dest="step_lo", type=int, default=4)
+    ap.add_argument("--step-hi", dest="step_hi", type=int, default=7)
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=256, help="instances of the CPU baseline sample")
+    ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true")
+    ap.add_argument("--skip-assembly", dest="skip_assembly", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

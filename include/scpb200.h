@@ -142,6 +142,25 @@ int scpb200_forward_u(const scpb200_dims *d, const double *g, const double *cter
                       double *U, void *stream);
 
 /*
+ * Delay-compensation prediction of IterClass (MPC_Iter.py:25-33: odeint of Model.py:61-87 over
+ * linspace(0, delay_x+dt+delay_u, steps) with the steering reference held at u_path[:, -1]).
+ * Classical RK4, nsub substeps per output interval (16 gives < 1e-9 m against the reference's LSODA).
+ *   in : x[B,nVeh,6] measured states, u_ref[B,nVeh], veh[B,nVeh,5] (Lf, Lr used), T seconds, steps >= 2
+ *   out: out[B,nVeh,steps,6]   (MPC_delay_compensation_trajectory[s,:,v]; the last sample is Iter.x0)
+ */
+int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *p, const double *x, const double *u_ref,
+                        const double *veh, double T, int32_t steps, int32_t nsub, double *out, void *stream);
+
+/*
+ * Closed-loop advance on the controller's own linear model (MPC_Iter.py:94-97): x0 <- Ad x0 + Bd u + Ed,
+ * u0 <- u, with u = U[b,0,v] clamped to |u| <= uMax and |u - u0| <= duLim as main.py:164-168 does.
+ * Used by the synthetic benchmark to close the loop between MPC steps without leaving the device.
+ *   in : abe[B,nVeh,48] (K1), U[B,Hp,nVeh] (K4)      in/out: x0[B,nVeh,6], u0[B,nVeh]
+ */
+int scpb200_advance_linear(const scpb200_dims *d, const double *abe, const double *U, double uMax, double duLim,
+                           double *x0, double *u0, void *stream);
+
+/*
  * K3 — replaces the third-party QP solve of SCP_controller.py:135-150 on the reference's own dense inputs
  * (the CVXOPT/Gurobi-replacement entry):   min 1/2 x'Px + q'x  s.t.  A x <= b,  lb <= x <= ub.
  *   in : n1, mc and P[B,n1,n1] q[B,n1] A[B,mc,n1] b[B,mc] lb[B,n1] ub[B,n1]   (only d->B is read from dims)

@@ -306,3 +306,11 @@ def scp_controller_batch(g, cterm, H, qv, gamma0, dsafe, u, dsafeExtra=1.0, uLim
             list(ex.map(lambda s: run(*s), spans))
     return dict(u=u, traj=traj, U=U, scp_iters=stats[:, 0].astype(np.int64), ipm_iters=stats[:, 1].astype(np.int64),
                 feasible=stats[:, 2].astype(bool), obj=stats[:, 3])
+
+
+def ode_predict(x, u_ref, Lf, Lr, T, steps=10, tol=1e-12):
+    """Delay-compensation prediction for one vehicle (MPC_Iter.py:25-33); returns [steps, 6]."""
+    out = np.empty((steps, 6))
+    lib().orc_ode_predict(_p(_c(x)), C.c_double(u_ref), C.c_double(Lf), C.c_double(Lr), C.c_double(T), C.c_int(steps),
+                          C.c_double(tol), _p(out))
+    return out

@@ -36,7 +36,7 @@ def default_params_py() -> Params:
     """The values scpb200_default_params() writes (kept in sync by tests/test_capi.py)."""
     import math
     p = Params()
-    p.dt, p.uLim, p.dsafeExtra, p.delta_tol = 0.4, 3.0 * math.pi / 180.0, 1.0, 1e-3
+    p.dt, p.uLim, p.dsafeExtra, p.delta_tol = 0.4, math.pi / 180.0 * 3.0, 1.0, 1e-3
     p.omega_weight, p.omega_ub, p.constraint_tol = 1e5, 1e25, 2 * 2.1 * 1e-3
     p.max_scp_iter, p.obstacle_eval_mode = 20, 0
     p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-10, 1e-10, 1e-9, 1e-12, 1e20
@@ -59,6 +59,8 @@ PROTOTYPES = {
     "scpb200_assemble_dense": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 15,
     "scpb200_qcqp_evaluate": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 16,
     "scpb200_forward_u": [C.POINTER(Dims)] + [_P] * 6,
+    "scpb200_ode_predict": [C.POINTER(Dims), C.POINTER(Params), _P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P, _P],
+    "scpb200_advance_linear": [C.POINTER(Dims), _P, _P, C.c_double, C.c_double, _P, _P, _P],
     "scpb200_qp_solve_dense": [C.POINTER(Dims), C.POINTER(Params), C.c_int32, C.c_int32] + [_P] * 13,
     "scpb200_scp_solve": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 19,
 }

@@ -1,0 +1,220 @@
+"""BatchSCP — the batched controller stage (MPCclass set-up -> fused SCP solve) on one B200.
+
+PyTorch is used for what it is good at here: owning device buffers, pinned host staging buffers and the CUDA
+stream.  All arithmetic happens in libscpb200.so (hand-written sm_100a kernels) behind the C ABI of
+include/scpb200.h; tensors cross that boundary as raw `data_ptr()` values.  There is no CPU fallback: constructing
+a BatchSCP without a CUDA device, or without the built library, raises.
+
+One BatchSCP instance serves B independent scenarios / noise samples of the same shape (nVeh, Hp, nObst, nPts);
+multi-GPU runs create one instance per rank over a contiguous slice of the global batch (see parallel.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import Dims, Params, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchSCP:
+    """Device-resident state of one batch.
+
+    Inputs (device, float64):   x0[B,nVeh,6] u0[B,nVeh] veh[B,nVeh,5]=(Lf,Lr,Q,Q_final,R) poly[B,nVeh,nPts,2]
+                                dsafe[B,nVeh,nVeh] (dsafe_obst[B,nVeh,nObst], obst[B,nObst,Hp,2])
+    K1 outputs:                 ref g cterm [B,nVeh,Hp,2]  H[B,nVeh,Hp,Hp]  qv[B,nVeh,Hp]  gamma0[B]  abe[B,nVeh,48]
+    K4 in/out:                  u[B,n] (warm start in, solution out)
+    K4 outputs:                 traj[B,Hp,2,nVeh] U[B,Hp,nVeh] log[B,max_scp_iter,10] scp_iters ipm_iters status obj max_violation
+    """
+
+    def __init__(self, B: int, nVeh: int, Hp: int, nObst: int = 0, nPts: int = 2, params: Optional[Params] = None,
+                 device: Optional[torch.device] = None, keep_log: bool = True):
+        self.lib = _capi.load()
+        if not torch.cuda.is_available() or self.lib.scpb200_device_count() < 1:
+            raise _capi.Scpb200Error("BatchSCP needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.B, self.nVeh, self.Hp, self.nObst, self.nPts = int(B), int(nVeh), int(Hp), int(nObst), int(nPts)
+        self.n = self.nVeh * self.Hp
+        self.n1 = self.n + 1
+        self.mc = self.Hp * (self.nVeh * (self.nVeh - 1) // 2 + self.nVeh * self.nObst)
+        self.dims = Dims(self.B, self.nVeh, self.Hp, self.nObst, self.nPts)
+        if params is None:
+            params = Params()
+            self.lib.scpb200_default_params(C.byref(params))
+        self.params = params
+        self.keep_log = keep_log
+        f64 = dict(dtype=torch.float64, device=self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        B_, V, Hp_ = self.B, self.nVeh, self.Hp
+        with torch.cuda.device(self.device):
+            self.x0 = torch.zeros(B_, V, 6, **f64)
+            self.u0 = torch.zeros(B_, V, **f64)
+            self.veh = torch.zeros(B_, V, 5, **f64)
+            self.poly = torch.zeros(B_, V, self.nPts, 2, **f64)
+            self.dsafe = torch.zeros(B_, V, V, **f64)
+            self.dsafe_obst = torch.zeros(B_, V, self.nObst, **f64) if self.nObst else None
+            self.obst = torch.zeros(B_, self.nObst, Hp_, 2, **f64) if self.nObst else None
+            self.ref = torch.zeros(B_, V, Hp_, 2, **f64)
+            self.g = torch.zeros(B_, V, Hp_, 2, **f64)
+            self.cterm = torch.zeros(B_, V, Hp_, 2, **f64)
+            self.H = torch.zeros(B_, V, Hp_, Hp_, **f64)
+            self.qv = torch.zeros(B_, V, Hp_, **f64)
+            self.gamma0 = torch.zeros(B_, **f64)
+            self.abe = torch.zeros(B_, V, 48, **f64)
+            self.setup_status = torch.zeros(B_, **i32)
+            self.u = torch.zeros(B_, self.n, **f64)
+            self.traj = torch.zeros(B_, Hp_, 2, V, **f64)
+            self.U = torch.zeros(B_, Hp_, V, **f64)
+            self.log = torch.zeros(B_, self.params.max_scp_iter, _capi.LOG_W, **f64) if keep_log else None
+            self.scp_iters = torch.zeros(B_, **i32)
+            self.ipm_iters = torch.zeros(B_, **i32)
+            self.status = torch.zeros(B_, **i32)
+            self.obj = torch.zeros(B_, **f64)
+            self.max_violation = torch.zeros(B_, **f64)
+            nbytes = C.c_size_t(0)
+            check(self.lib.scpb200_workspace_bytes(C.byref(self.dims), C.byref(nbytes)), "scpb200_workspace_bytes")
+            self.ws = torch.zeros(max(int(nbytes.value), 256), dtype=torch.uint8, device=self.device)
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def plan(self):
+        out = (C.c_int64 * 5)()
+        check(self.lib.scpb200_scp_plan(C.byref(self.dims), out), "scpb200_scp_plan")
+        return dict(grid=out[0], threads=out[1], smem_bytes=out[2], S_in_shared=bool(out[3]), sms=out[4])
+
+    def load_inputs(self, x0=None, u0=None, veh=None, poly=None, dsafe=None, dsafe_obst=None, obst=None, u=None):
+        """Copy whichever inputs are given (numpy or torch, host or device) into the device buffers."""
+        for name, val in (("x0", x0), ("u0", u0), ("veh", veh), ("poly", poly), ("dsafe", dsafe),
+                          ("dsafe_obst", dsafe_obst), ("obst", obst), ("u", u)):
+            if val is None:
+                continue
+            dst = getattr(self, name)
+            src = torch.as_tensor(val, dtype=torch.float64)
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------------ kernels
+    def setup(self):
+        """K1: MPCclass.__init__ (MPC_Iter.py:57-97) + reference sampling for the whole batch."""
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_mpc_setup(
+                C.byref(self.dims), C.byref(self.params), _ptr(self.x0), _ptr(self.u0), _ptr(self.veh), _ptr(self.poly),
+                _ptr(self.ref), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv), _ptr(self.gamma0),
+                _ptr(self.abe), _ptr(self.setup_status), self._stream()), "scpb200_mpc_setup")
+        self.kernel_launches += 1
+
+    def solve(self):
+        """K4: SCPcontroller.SCP_controller (SCP_controller.py:40-197) for the whole batch; u is warm start and result."""
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_scp_solve(
+                C.byref(self.dims), C.byref(self.params), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv),
+                _ptr(self.gamma0), _ptr(self.dsafe), _ptr(self.dsafe_obst), _ptr(self.obst), _ptr(self.u),
+                _ptr(self.traj), _ptr(self.U), _ptr(self.log), _ptr(self.scp_iters), _ptr(self.ipm_iters),
+                _ptr(self.status), _ptr(self.obj), _ptr(self.max_violation), _ptr(self.ws), self._stream()),
+                "scpb200_scp_solve")
+        self.kernel_launches += 1
+
+    def controller_step(self):
+        """The controller stage of one MPC step: K1 then K4 (what main.py:131-134 does per step)."""
+        self.setup()
+        self.solve()
+
+    def evaluate(self, u: Optional[torch.Tensor] = None, want_ci: bool = False):
+        """QCQP_evaluate (SCP_controller.py:215-265) for the batch at u (default: the current solution)."""
+        u = self.u if u is None else u
+        f64 = dict(dtype=torch.float64, device=self.device)
+        obj, mv, sv = torch.zeros(self.B, **f64), torch.zeros(self.B, **f64), torch.zeros(self.B, **f64)
+        feas = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        ci = torch.zeros(self.B, self.nVeh, self.nVeh, self.Hp, **f64) if want_ci else None
+        cio = torch.zeros(self.B, self.nVeh, self.nObst, self.Hp, **f64) if (want_ci and self.nObst) else None
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_qcqp_evaluate(
+                C.byref(self.dims), C.byref(self.params), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv),
+                _ptr(self.gamma0), _ptr(u), _ptr(self.dsafe), _ptr(self.dsafe_obst), _ptr(self.obst), _ptr(obj), _ptr(mv),
+                _ptr(sv), _ptr(feas), _ptr(ci), _ptr(cio), self._stream()), "scpb200_qcqp_evaluate")
+        self.kernel_launches += 1
+        return dict(obj=obj, max_violation=mv, sum_violations=sv, feasible=feas, ci=ci, ci_obst=cio)
+
+    def assemble_dense(self, ubar: Optional[torch.Tensor] = None):
+        """K2: the dense QP (P,q,Aineq,bineq,lb,ub) of SCP_controller.py:93-128 about ubar (default: current u)."""
+        ubar = self.u if ubar is None else ubar
+        f64 = dict(dtype=torch.float64, device=self.device)
+        B, n1, mc = self.B, self.n1, self.mc
+        out = dict(P=torch.empty(B, n1, n1, **f64), q=torch.empty(B, n1, **f64), A=torch.empty(B, mc, n1, **f64),
+                   b=torch.empty(B, mc, **f64), lb=torch.empty(B, n1, **f64), ub=torch.empty(B, n1, **f64))
+        self.assemble_dense_into(ubar, out)
+        return out
+
+    def assemble_dense_into(self, ubar, out):
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_assemble_dense(
+                C.byref(self.dims), C.byref(self.params), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv),
+                _ptr(ubar), _ptr(self.dsafe), _ptr(self.dsafe_obst), _ptr(self.obst), _ptr(out["P"]), _ptr(out["q"]),
+                _ptr(out["A"]), _ptr(out["b"]), _ptr(out["lb"]), _ptr(out["ub"]), self._stream()), "scpb200_assemble_dense")
+        self.kernel_launches += 1
+
+    def forward_u(self, u: Optional[torch.Tensor] = None):
+        u = self.u if u is None else u
+        f64 = dict(dtype=torch.float64, device=self.device)
+        traj, U = torch.empty(self.B, self.Hp, 2, self.nVeh, **f64), torch.empty(self.B, self.Hp, self.nVeh, **f64)
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_forward_u(C.byref(self.dims), _ptr(self.g), _ptr(self.cterm), _ptr(u), _ptr(traj), _ptr(U),
+                                             self._stream()), "scpb200_forward_u")
+        self.kernel_launches += 1
+        return traj, U
+
+    def advance_linear(self, uMax: float, duLim: float):
+        """Close the loop on the controller's linear model: x0 <- Ad x0 + Bd U[0] + Ed, u0 <- U[0] (clamped)."""
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_advance_linear(C.byref(self.dims), _ptr(self.abe), _ptr(self.U), C.c_double(uMax),
+                                                  C.c_double(duLim), _ptr(self.x0), _ptr(self.u0), self._stream()),
+                  "scpb200_advance_linear")
+        self.kernel_launches += 1
+
+    def ode_predict(self, x: torch.Tensor, u_ref: torch.Tensor, T: float, steps: int = 10, nsub: int = 16):
+        """Delay-compensation prediction (MPC_Iter.py:25-33) for the batch; returns [B,nVeh,steps,6]."""
+        out = torch.empty(self.B, self.nVeh, steps, 6, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_ode_predict(C.byref(self.dims), C.byref(self.params), _ptr(x), _ptr(u_ref), _ptr(self.veh),
+                                               C.c_double(T), C.c_int32(steps), C.c_int32(nsub), _ptr(out), self._stream()),
+                  "scpb200_ode_predict")
+        self.kernel_launches += 1
+        return out
+
+
+def qp_solve_dense(P, q, A, b, lb, ub, params: Optional[Params] = None):
+    """The CVXOPT/Gurobi-replacement entry on dense device tensors: P[B,n1,n1] q[B,n1] A[B,mc,n1] b[B,mc] lb,ub[B,n1].
+
+    Returns dict(x[B,n1], fval[B], iters[B], status[B], zA[B,mc]) of device tensors."""
+    lib = _capi.load()
+    if not torch.cuda.is_available():
+        raise _capi.Scpb200Error("qp_solve_dense needs a CUDA device; there is no CPU fallback")
+    dev = P.device
+    B, n1, mc = P.shape[0], P.shape[1], A.shape[1]
+    if params is None:
+        params = Params()
+        lib.scpb200_default_params(C.byref(params))
+    f64 = dict(dtype=torch.float64, device=dev)
+    args = [t.contiguous() for t in (P, q, A, b, lb, ub)]
+    x, fval = torch.empty(B, n1, **f64), torch.empty(B, **f64)
+    iters, status = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+    zA = torch.empty(B, mc, **f64)
+    with torch.cuda.device(dev):
+        nbytes = C.c_size_t(0)
+        check(lib.scpb200_qp_workspace_bytes(C.c_int32(n1), C.c_int32(mc), C.byref(nbytes)), "scpb200_qp_workspace_bytes")
+        ws = torch.zeros(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+        d = Dims(B, 1, 1, 0, 2)
+        check(lib.scpb200_qp_solve_dense(C.byref(d), C.byref(params), C.c_int32(n1), C.c_int32(mc), *[_ptr(t) for t in args],
+                                         _ptr(x), _ptr(fval), _ptr(iters), _ptr(status), _ptr(zA), _ptr(ws),
+                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "scpb200_qp_solve_dense")
+        torch.cuda.current_stream(dev).synchronize()      # ws must outlive the kernel
+    return dict(x=x, fval=fval, iters=iters, status=status, zA=zA)

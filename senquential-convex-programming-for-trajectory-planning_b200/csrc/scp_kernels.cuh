@@ -335,6 +335,64 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     CTA_PHASE_END
 }
 
+// ================================================================================================ ODE prediction
+// Classical RK4 of Model.py:61-87 with constant steering reference over `T` seconds, `nsub` substeps per output
+// interval, writing `steps` samples (t = 0 .. T inclusive) — the delay-compensation prediction of IterClass
+// (MPC_Iter.py:25-33: odeint over linspace(0, delay_x+dt+delay_u, 10)).  With noise_sigma > 0 every RHS
+// evaluation adds N(0, sigma) to (dx, dy) (Model.py:84-86) from the keyed Philox stream
+// (counter = noise_counter * 65536 + stage index).
+SCP_HDFN void scp_ode_predict_vehicle(const double *x_in, double u_ref, double Lf, double Lr, double T, int steps,
+                                      int nsub, double noise_sigma, uint64_t seed, uint32_t instance, uint32_t vehicle,
+                                      uint32_t noise_counter, double *out /*[steps][6]*/)
+{
+    double x[6], k1[6], k2[6], k3[6], k4[6], xt[6];
+    for (int i = 0; i < 6; ++i) { x[i] = x_in[i]; out[i] = x_in[i]; }
+    const double h = T / (double)((steps - 1) * nsub);
+    uint32_t stage = 0;
+    for (int s = 1; s < steps; ++s) {
+        for (int j = 0; j < nsub; ++j) {
+            double nz[2];
+#define SCP_RHS(xx, kk)                                                                         \
+    scp_bicycle_rhs(xx, u_ref, Lf, Lr, kk);                                                     \
+    if (noise_sigma > 0.0) {                                                                    \
+        scp_noise_pair(seed, instance, vehicle, noise_counter * 65536u + (stage++), nz);        \
+        kk[0] += noise_sigma * nz[0];                                                           \
+        kk[1] += noise_sigma * nz[1];                                                           \
+    }
+            SCP_RHS(x, k1)
+            for (int i = 0; i < 6; ++i) xt[i] = x[i] + 0.5 * h * k1[i];
+            SCP_RHS(xt, k2)
+            for (int i = 0; i < 6; ++i) xt[i] = x[i] + 0.5 * h * k2[i];
+            SCP_RHS(xt, k3)
+            for (int i = 0; i < 6; ++i) xt[i] = x[i] + h * k3[i];
+            SCP_RHS(xt, k4)
+#undef SCP_RHS
+            for (int i = 0; i < 6; ++i) x[i] += h / 6.0 * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+        }
+        for (int i = 0; i < 6; ++i) out[s * 6 + i] = x[i];
+    }
+}
+
+// ================================================================================================ linear advance
+// x <- Ad x + Bd u_applied + Ed, u0 <- u_applied with u_applied = U[0, v] clamped as main.py:164-168 does
+// (|u| <= uMax, |u - u0| <= duLim).  This is the linearised plant the controller itself predicts with
+// (MPC_Iter.py:94-97); the synthetic benchmark closes the loop with it so that the timed region isolates the
+// controller stage.  The non-linear plant step of main.py:176-191 is scpb200_plant_step.
+SCP_HDFN void scp_advance_vehicle(const double *abe, double u_cmd, double uMax, double duLim, double *x, double *u0)
+{
+    double ua = u_cmd;
+    ua = fmin(ua, uMax); ua = fmax(ua, -uMax);
+    ua = fmin(ua, *u0 + duLim); ua = fmax(ua, *u0 - duLim);
+    double xn[6];
+    for (int i = 0; i < 6; ++i) {
+        double acc = abe[42 + i] + abe[36 + i] * ua;
+        for (int j = 0; j < 6; ++j) acc += abe[i * 6 + j] * x[j];
+        xn[i] = acc;
+    }
+    for (int i = 0; i < 6; ++i) x[i] = xn[i];
+    *u0 = ua;
+}
+
 // ================================================================================================ shared pieces
 // pos[(v,k)] = cterm_v(k) + sum_{a<=k} g_v[k-a] u_v[a]      (forward_U, SCP_controller.py:199-213)
 SCP_FN void scp_positions(Cta &cta, int nVeh, int Hp, const double *g, const double *cterm, const double *u, double *pos)

@@ -28,7 +28,7 @@ extern "C" void scpb200_default_params(scpb200_params *p)
 {
     memset(p, 0, sizeof *p);
     p->dt = 0.4;
-    p->uLim = 3.0 * 3.14159265358979323846 / 180.0;
+    p->uLim = 3.14159265358979323846 / 180.0 * 3.0;   /* Scenarios.py:53, evaluated in the reference's order */
     p->dsafeExtra = 1.0;
     p->delta_tol = 1e-3;
     p->omega_weight = 1e5;
@@ -153,6 +153,28 @@ __global__ void __launch_bounds__(128) k_forward(scpb200_dims d, const double *g
         traj[(((size_t)b * Hp + k) * 2 + 0) * nVeh + v] = px;
         traj[(((size_t)b * Hp + k) * 2 + 1) * nVeh + v] = py;
         if (U) U[((size_t)b * Hp + k) * nVeh + v] = uv[k];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ode_predict(scpb200_dims d, scpb200_params p, const double *x, const double *u_ref,
+                                                     const double *veh, double T, int steps, int nsub, double *out)
+{
+    const int tot = d.B * d.nVeh;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int b = e / d.nVeh, v = e - b * d.nVeh;
+        scp_ode_predict_vehicle(x + (size_t)e * 6, u_ref[e], veh[(size_t)e * 5], veh[(size_t)e * 5 + 1], T, steps, nsub,
+                                p.noise_sigma, p.seed, p.instance0 + (uint32_t)b, (uint32_t)v, p.noise_counter,
+                                out + (size_t)e * steps * 6);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_advance_linear(scpb200_dims d, const double *abe, const double *U, double uMax,
+                                                        double duLim, double *x0, double *u0)
+{
+    const int tot = d.B * d.nVeh;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int b = e / d.nVeh, v = e - b * d.nVeh;
+        scp_advance_vehicle(abe + (size_t)e * 48, U[(size_t)b * d.Hp * d.nVeh + v], uMax, duLim, x0 + (size_t)e * 6, u0 + e);
     }
 }
 
@@ -364,6 +386,35 @@ extern "C" int scpb200_forward_u(const scpb200_dims *d, const double *g, const d
     const size_t tot = (size_t)d->B * d->nVeh * d->Hp;
     const int grid = (int)((tot + 127) / 128 < 65535 ? (tot + 127) / 128 : 65535);
     k_forward<<<grid, 128, 0, (cudaStream_t)stream>>>(*d, g, cterm, u, traj, U);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *p, const double *x, const double *u_ref,
+                                   const double *veh, double T, int32_t steps, int32_t nsub, double *out, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !x || !u_ref || !veh || !out || steps < 2 || nsub < 1 || !(T > 0.0))
+        return set_err(SCPB200_ERR_ARG, "scpb200_ode_predict: bad argument");
+    if (d->B == 0) return 0;
+    const int tot = d->B * d->nVeh;
+    const int grid = (tot + 63) / 64 < 65535 ? (tot + 63) / 64 : 65535;
+    k_ode_predict<<<grid, 64, 0, (cudaStream_t)stream>>>(*d, *p, x, u_ref, veh, T, steps, nsub, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_advance_linear(const scpb200_dims *d, const double *abe, const double *U, double uMax, double duLim,
+                                      double *x0, double *u0, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!abe || !U || !x0 || !u0) return set_err(SCPB200_ERR_ARG, "scpb200_advance_linear: NULL argument");
+    if (d->B == 0) return 0;
+    const int tot = d->B * d->nVeh;
+    const int grid = (tot + 127) / 128 < 65535 ? (tot + 127) / 128 : 65535;
+    k_advance_linear<<<grid, 128, 0, (cudaStream_t)stream>>>(*d, abe, U, uMax, duLim, x0, u0);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -119,6 +119,16 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
     return 0;
 }
 
+extern "C" int emu_ode_predict(const scpb200_dims *d, const scpb200_params *p, const double *x, const double *u_ref,
+                               const double *veh, double T, int32_t steps, int32_t nsub, double *out)
+{
+    for (int e = 0; e < d->B * d->nVeh; ++e)
+        scp_ode_predict_vehicle(x + (size_t)e * 6, u_ref[e], veh[(size_t)e * 5], veh[(size_t)e * 5 + 1], T, steps, nsub,
+                                p->noise_sigma, p->seed, p->instance0 + (uint32_t)(e / d->nVeh), (uint32_t)(e % d->nVeh),
+                                p->noise_counter, out + (size_t)e * steps * 6);
+    return 0;
+}
+
 extern "C" size_t emu_scp_shared_bytes(int nVeh, int Hp, int nObst, int S_in_shared)
 {
     return scp_shared_doubles(nVeh, Hp, nObst, S_in_shared != 0) * 8;

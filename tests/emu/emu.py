@@ -128,3 +128,13 @@ def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=N
     lib().emu_scp_solve(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(gamma0), _d(dsafe), _d(dso), _d(ob),
                         _d(u), _d(traj), _d(U), _d(log), _i(si), _i(ii), _i(st), _d(obj), _d(mv))
     return dict(u=u, traj=traj, U=U, log=log, scp_iters=si, ipm_iters=ii, status=st, obj=obj, max_violation=mv)
+
+
+def ode_predict(x, u_ref, veh, T, steps, nsub, params):
+    x, u_ref, veh = _c(x), _c(u_ref), _c(veh)
+    B, nVeh = x.shape[0], x.shape[1]
+    d = Dims(B, nVeh, 1, 0, 2)
+    out = np.zeros((B, nVeh, steps, 6))
+    lib().emu_ode_predict(C.byref(d), C.byref(params), _d(x), _d(u_ref), _d(veh), C.c_double(T), C.c_int32(steps),
+                          C.c_int32(nsub), _d(out))
+    return out

@@ -1,0 +1,314 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libscpb200.so via the ctypes layer), against the
+oracle and the reference's golden vectors.  Run on a B200 with `pytest -m gpu`.
+
+Tolerances are the north-star's: per SCP iteration (teacher-forced) relative objective <= 1e-6, |u - u*|_inf <= 1e-5,
+constraint violation <= 1e-6; free-running trajectories within 1e-4 m.  The tests assert a 10x tighter 1e-6 on u."""
+import ctypes as C
+import glob
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_setup_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+PKG = "senquential-convex-programming-for-trajectory-planning_b200"
+STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+NOT50 = [f for f in STEP_FILES if "hp50" not in f]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    capi = importlib.import_module(PKG + "._capi")
+    batch = importlib.import_module(PKG + ".batch")
+    scen = importlib.import_module(PKG + ".scenarios")
+    return dict(torch=torch, capi=capi, batch=batch, scen=scen)
+
+
+def make_batch(mods, G, B=1, **pkw):
+    capi, batch = mods["capi"], mods["batch"]
+    p = capi.Params()
+    capi.load().scpb200_default_params(C.byref(p))
+    p.dt, p.uLim, p.dsafeExtra = float(G["sc_dt"]), float(G["sc_uLim"]), float(G["sc_dsafeExtra"])
+    for k, v in pkw.items():
+        setattr(p, k, v)
+    bs = batch.BatchSCP(B, int(G["sc_nVeh"]), int(G["sc_Hp"]), params=p)
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    rep = lambda a: np.repeat(a, B, axis=0)
+    bs.load_inputs(x0=rep(x0), u0=rep(u0), veh=rep(veh), poly=rep(poly), dsafe=rep(G["sc_dsafeVehicles"][None]))
+    return bs
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def test_library_loaded_is_the_in_tree_cuda_build(mods):
+    lib = mods["capi"].load()
+    assert os.path.samefile(mods["capi"].LIB_PATH, os.path.join(os.path.dirname(GOLDEN), "..", PKG, "libscpb200.so"))
+    assert lib.scpb200_device_count() >= 1
+    assert lib.scpb200_version() == 100
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_setup_kernel(mods, oracle, fname):
+    """K1 vs the reference's MPCclass / IterClass arrays (golden) and the oracle, 1e-12 relative."""
+    G = load_golden(fname)
+    Hp, nVeh = int(G["sc_Hp"]), int(G["sc_nVeh"])
+    bs = make_batch(mods, G)
+    bs.setup()
+    O = oracle.mpc_setup(*golden_setup_inputs(G), Hp=Hp, dt=float(G["sc_dt"]))
+    assert (host(bs.setup_status) == 0).all()
+    for k in ["ref", "g", "cterm", "H", "abe"]:
+        assert np.abs(host(getattr(bs, k)) - O[k]).max() <= 1e-12 * np.abs(O[k]).max(), k
+    qscale = 2 * 20 * Hp * np.abs(O["g"]).max() * np.abs(O["ref"]).max()
+    assert np.abs(host(bs.qv) - O["qv"]).max() <= 1e-13 * qscale
+    assert abs(host(bs.gamma0)[0] - O["gamma0"][0]) <= 1e-12 * max(1.0, abs(O["gamma0"][0])) * Hp
+    for v in range(nVeh):
+        assert np.abs(host(bs.H)[0, v] - G["Phi_0"][:, :, v]).max() <= 1e-12 * np.abs(G["Phi_0"]).max()
+        assert np.abs(host(bs.cterm)[0, v].ravel() - G["const_term"][:, v]).max() <= 1e-12 * np.abs(G["const_term"]).max()
+        assert np.abs(host(bs.ref)[0, v] - G["RefPts"][:, :, v]).max() <= 1e-12 * np.abs(G["RefPts"]).max()
+        assert np.abs(host(bs.abe)[0, v, :36].reshape(6, 6) - G["A"][:, :, v]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_assemble_dense_kernel(mods, fname):
+    """K2 vs the dense P, q, Aineq, bineq, lb, ub the reference logged for the same ubar."""
+    G = load_golden(fname)
+    torch = mods["torch"]
+    bs = make_batch(mods, G)
+    bs.setup()
+    for it in sorted(int(k.split("_")[1]) for k in G if k.startswith("Aineq_")):
+        ubar = torch.as_tensor(G["prev_u"][it][None], device=bs.device)
+        D = {k: host(v)[0] for k, v in bs.assemble_dense(ubar).items()}
+        assert np.abs(D["P"] - G[f"P_{it}"]).max() <= 1e-12 * np.abs(G[f"P_{it}"]).max()
+        assert np.abs(D["A"] - G[f"Aineq_{it}"]).max() <= 1e-11 * np.abs(G[f"Aineq_{it}"]).max()
+        assert (D["A"][G[f"Aineq_{it}"] == 0] == 0).all()
+        assert np.abs(D["b"] - G[f"bineq_{it}"]).max() <= 1e-11 * np.abs(G[f"bineq_{it}"]).max()
+        qscale = 2 * 20 * int(G["sc_Hp"]) * np.abs(host(bs.g)).max() * np.abs(host(bs.ref)).max()
+        assert np.abs(D["q"] - G[f"q_{it}"]).max() <= 1e-13 * qscale
+        np.testing.assert_array_equal(D["lb"], G[f"lb_{it}"])
+        np.testing.assert_array_equal(D["ub"], G[f"ub_{it}"])
+
+
+@pytest.mark.parametrize("fname", STEP_FILES)
+def test_evaluate_and_forward_kernels(mods, fname):
+    G = load_golden(fname)
+    torch = mods["torch"]
+    bs = make_batch(mods, G)
+    bs.setup()
+    u = torch.as_tensor(G["u_final"][None], device=bs.device)
+    ev = {k: (host(v) if v is not None else None) for k, v in bs.evaluate(u, want_ci=True).items()}
+    assert bool(ev["feasible"][0]) == bool(G["eval_feasible"])
+    assert abs(ev["obj"][0] - float(G["eval_obj"])) <= 1e-9 * max(1.0, abs(float(G["eval_obj"])))
+    assert abs(ev["max_violation"][0] - float(G["eval_max_violation"])) < 1e-9
+    assert abs(ev["sum_violations"][0] - float(G["eval_sum_violations"])) < 1e-9
+    fin = np.isfinite(G["eval_ci"])
+    assert (np.isfinite(ev["ci"][0]) == fin).all()
+    assert np.abs(ev["ci"][0][fin] - G["eval_ci"][fin]).max() < 1e-9
+    traj, U = bs.forward_u(u)
+    assert np.abs(host(traj)[0] - G["Traj"]).max() < 1e-10
+    assert np.abs(host(U)[0] - G["U"]).max() == 0.0
+
+
+def _dense_qps(oracle, G, its):
+    O = oracle.mpc_setup(*golden_setup_inputs(G), Hp=int(G["sc_Hp"]), dt=float(G["sc_dt"]))
+    qps = [oracle.assemble_dense(O["g"][0], O["cterm"][0], O["H"][0], O["qv"][0], G["prev_u"][it], G["sc_dsafeVehicles"],
+                                 float(G["sc_dsafeExtra"]), float(G["sc_uLim"])) for it in its]
+    return [np.stack([qp[k] for qp in qps]) for k in range(6)]
+
+
+@pytest.mark.parametrize("fname", NOT50)
+def test_dense_qp_entry_vs_extended_precision_minimiser(mods, oracle, fname):
+    """K3 (the CVXOPT-replacement entry) on the reference's dense QPs of every SCP iteration of the golden step."""
+    G = load_golden(fname)
+    torch = mods["torch"]
+    its = list(range(int(G["scp_iters"])))
+    P, q, A, b, lb, ub = _dense_qps(oracle, G, its)
+    dev = torch.device("cuda")
+    r = mods["batch"].qp_solve_dense(*[torch.as_tensor(a, device=dev) for a in (P, q, A, b, lb, ub)])
+    x, fval, st, zA = host(r["x"]), host(r["fval"]), host(r["status"]), host(r["zA"])
+    for j, it in enumerate(its):
+        xs = G["x"][it]
+        assert st[j] == 0, (it, st[j], host(r["iters"])[j])
+        assert np.abs(x[j] - xs).max() < 1e-6
+        f_ref = 0.5 * xs @ P[j] @ xs + q[j] @ xs
+        assert abs(fval[j] - f_ref) <= 1e-6 * max(1.0, abs(f_ref))
+        assert max((A[j] @ x[j] - b[j]).max(), (lb[j] - x[j]).max(), (x[j][:-1] - ub[j][:-1]).max()) <= 1e-6
+        assert (zA[j] >= 0).all()
+
+
+@pytest.mark.parametrize("fname", NOT50)
+def test_scp_kernel_teacher_forced(mods, fname):
+    """K4, one QP per instance from the reference's own linearisation points (batch = the SCP iterations)."""
+    G = load_golden(fname)
+    capi = mods["capi"]
+    nit = int(G["scp_iters"])
+    bs = make_batch(mods, G, B=nit, max_scp_iter=1)
+    bs.load_inputs(u=G["prev_u"][:nit])
+    bs.controller_step()
+    u, log, st = host(bs.u), host(bs.log), host(bs.status)
+    for it in range(nit):
+        assert np.abs(u[it] - G["x"][it][:-1]).max() < 1e-6, it
+        assert abs(log[it, 0, 0] - G["slack"][it]) < 1e-6
+        assert abs(log[it, 0, 1] - G["SCP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][it]))
+        assert abs(log[it, 0, 2] - G["QCQP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["QCQP_ObjVal"][it]))
+        assert bool(log[it, 0, 5]) == bool(G["feasible"][it])
+        assert (st[it] & (capi.ST_QP_MAXITER | capi.ST_QP_PIVOT)) == 0
+
+
+def test_scp_kernel_hp50_first_iteration(mods):
+    """Hp = 50 (n1 = 401, normal matrix in the L2-resident workspace): first SCP iteration, teacher-forced."""
+    G = load_golden("circle8_hp50_step3.npz")
+    bs = make_batch(mods, G, B=1, max_scp_iter=1)
+    bs.load_inputs(u=G["prev_u"][:1])
+    assert not bs.plan()["S_in_shared"]
+    bs.controller_step()
+    assert np.abs(host(bs.u)[0] - G["x"][0][:-1]).max() < 1e-6
+    assert abs(host(bs.log)[0, 0, 1] - G["SCP_ObjVal"][0]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][0]))
+
+
+@pytest.mark.parametrize("fname", NOT50)
+def test_scp_kernel_free_running(mods, fname):
+    G = load_golden(fname)
+    capi = mods["capi"]
+    bs = make_batch(mods, G)
+    bs.load_inputs(u=G["u_warm"][None])
+    bs.controller_step()
+    its = int(host(bs.scp_iters)[0])
+    assert bool(host(bs.log)[0, its - 1, 5]) == bool(G["feasible"][-1])
+    if int(G["scp_iters"]) <= 5:
+        assert its == int(G["scp_iters"])
+        assert np.abs(host(bs.u)[0] - G["u_final"]).max() < 1e-6
+        assert np.abs(host(bs.traj)[0] - G["Traj"]).max() < 1e-4
+        assert np.abs(host(bs.U)[0] - G["U"]).max() < 1e-6
+    else:
+        assert abs(its - int(G["scp_iters"])) <= 2
+    assert (host(bs.status)[0] & (capi.ST_SCP_MAXITER | capi.ST_INFEASIBLE)) == 0
+
+
+def test_closed_loop_rollout_against_reference_run(mods):
+    """The reference's own 50-step closed loop (golden run): at every MPC step feed the reference's measured
+    state (x0, u0) and warm start; controller outputs must match where the SCP map is stable, and the number of
+    QPs solved over the run must match the reference's 124 within the symmetric-step slack."""
+    R = load_golden("circle8_hp10_run.npz")
+    G0 = load_golden("circle8_hp10_step0.npz")
+    nsteps = R["x0"].shape[0]
+    bs = make_batch(mods, G0, B=nsteps)
+    veh = np.stack([G0["sc_Lf"], G0["sc_Lr"], G0["sc_Q"], G0["sc_Q_final"], G0["sc_R"]], axis=1)
+    warm = np.vstack([np.zeros((1, 80)), R["u_final"][:-1]])
+    bs.load_inputs(x0=R["x0"], u0=R["u0"], veh=np.repeat(veh[None], nsteps, 0), u=warm)
+    bs.controller_step()
+    its, u = host(bs.scp_iters), host(bs.u)
+    stable = R["scp_iters"] <= 5
+    assert (its[stable] == R["scp_iters"][stable]).all()
+    assert np.abs(u[stable] - R["u_final"][stable]).max() < 1e-6
+    assert np.abs(host(bs.traj)[stable] - R["Traj"][stable]).max() < 1e-4
+    assert abs(int(its.sum()) - int(R["qp_total"])) <= 3
+    assert (host(bs.status) & 8 == 0).all()                  # 50/50 feasible
+
+
+def test_batch_1024_against_oracle_and_invariants(mods, oracle):
+    """BASELINE config 2 size (default scenario x1024, perturbed): every instance against the CPU oracle run in
+    double with the same tolerances on a subset, and size-independent invariants on the full batch."""
+    scen, capi = mods["scen"], mods["capi"]
+    B = 1024
+    cb = scen.circle_batch(B, nVeh=8, Hp=10, step_lo=5, step_hi=7)
+    p = capi.Params()
+    capi.load().scpb200_default_params(C.byref(p))
+    bs = mods["batch"].BatchSCP(B, 8, 10, params=p)
+    bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, 80)))
+    bs.controller_step()
+    u, its, st = host(bs.u), host(bs.scp_iters), host(bs.status)
+    assert ((st & (capi.ST_QP_MAXITER | capi.ST_SETUP)) == 0).all()
+    assert np.abs(u).max() <= p.uLim + 1e-9                                    # box satisfied
+    # evaluate kernel agrees with the solver's own bookkeeping
+    ev = bs.evaluate()
+    assert np.abs(host(ev["obj"]) - host(bs.obj)).max() <= 1e-9 * max(1.0, np.abs(host(bs.obj)).max())
+    # idempotence: re-solving from the converged u stops after one QP for converged instances and keeps u
+    conv = (st & capi.ST_SCP_MAXITER) == 0
+    u_first = u.copy()
+    bs.solve()
+    assert (host(bs.scp_iters)[conv] <= 2).all()
+    assert np.abs(host(bs.u)[conv] - u_first[conv]).max() < 1e-5
+    # subset against the oracle (double precision, same stopping rule), free-running
+    idx = np.arange(0, B, 16)
+    S = oracle.mpc_setup(cb.x0[idx], cb.u0[idx], cb.veh[idx], cb.poly[idx], Hp=10, dt=0.4)
+    O = oracle.scp_controller_batch(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], cb.dsafe[idx], np.zeros((len(idx), 80)),
+                                    opts=dict(abstol=1e-10, reltol=1e-10, feastol=1e-9), threads=os.cpu_count() or 1)
+    same = (O["scp_iters"] == its[idx]) & (O["scp_iters"] <= 5)
+    assert same.sum() >= len(idx) // 2
+    assert np.abs(u_first[idx][same] - O["u"][same]).max() < 1e-5
+
+
+def test_results_do_not_depend_on_batch_position(mods):
+    """Sharding determinism: an instance's result is bit-identical wherever it sits in a batch."""
+    scen = mods["scen"]
+    cb = scen.circle_batch(96, step_lo=6, step_hi=7)
+    def run(order):
+        bs = mods["batch"].BatchSCP(len(order), 8, 10)
+        bs.load_inputs(x0=cb.x0[order], u0=cb.u0[order], veh=cb.veh[order], poly=cb.poly[order], dsafe=cb.dsafe[order],
+                       u=np.zeros((len(order), 80)))
+        bs.controller_step()
+        return host(bs.u), host(bs.scp_iters)
+    u_a, it_a = run(np.arange(96))
+    perm = np.random.default_rng(0).permutation(96)
+    u_b, it_b = run(perm)
+    np.testing.assert_array_equal(u_a[perm], u_b)
+    np.testing.assert_array_equal(it_a[perm], it_b)
+    u_c, _ = run(np.arange(48, 96))                          # a "second rank's" shard
+    np.testing.assert_array_equal(u_a[48:], u_c)
+
+
+def test_ode_predict_and_linear_advance(mods, oracle):
+    G = load_golden("circle8_hp10_step10.npz")
+    torch = mods["torch"]
+    bs = make_batch(mods, G)
+    T = float(G["sc_delay_x"] + G["sc_dt"] + G["sc_delay_u"])
+    xm = torch.as_tensor(G["x_measured"][None], device=bs.device)
+    ur = torch.as_tensor(G["u_path"][:, -1][None], device=bs.device)
+    Y = host(bs.ode_predict(xm, ur, T, steps=10, nsub=16))[0]                   # [nVeh,10,6]
+    assert np.abs(np.transpose(Y, (1, 2, 0)) - G["delay_traj"]).max() < 1e-7     # the reference's LSODA is ~1e-8
+    O = np.array([oracle.ode_predict(G["x_measured"][v], G["u_path"][v, -1], G["sc_Lf"][v], G["sc_Lr"][v], T) for v in range(8)])
+    assert np.abs(Y - O).max() < 1e-10
+    assert np.abs(Y[:, -1] - G["x0"]).max() < 1e-7
+    bs.setup()
+    bs.load_inputs(u=G["u_final"][None])
+    traj, U = bs.forward_u()
+    bs.U.copy_(U)
+    x_before, abe = host(bs.x0)[0].copy(), host(bs.abe)[0]
+    bs.advance_linear(float(G["sc_mechanicalSteeringLimit"]), float(G["sc_duLim"]))
+    for v in range(8):
+        ua = np.clip(G["U"][0, v], -G["sc_mechanicalSteeringLimit"], G["sc_mechanicalSteeringLimit"])
+        ua = np.clip(ua, G["u0"][v, 0] - G["sc_duLim"], G["u0"][v, 0] + G["sc_duLim"])
+        xn = abe[v, :36].reshape(6, 6) @ x_before[v] + abe[v, 36:42] * ua + abe[v, 42:48]
+        assert np.abs(host(bs.x0)[0, v] - xn).max() < 1e-12
+        assert abs(host(bs.u0)[0, v] - ua) < 1e-15
+
+
+def test_noise_is_keyed_per_instance_and_reproducible(mods, oracle):
+    G = load_golden("circle8_hp10_step10.npz")
+    bs = make_batch(mods, G, B=4, noise_sigma=3e-6, seed=99, instance0=5, noise_counter=2)
+    bs.setup()
+    x0, u0, veh, poly = (np.repeat(a, 4, axis=0) for a in golden_setup_inputs(G))
+    O = oracle.mpc_setup(x0, u0, veh, poly, Hp=10, dt=0.4, noise_sigma=3e-6, seed=99, instance0=5, noise_counter=2)
+    assert np.abs(host(bs.cterm) - O["cterm"]).max() <= 1e-12 * np.abs(O["cterm"]).max()
+    assert np.abs(host(bs.cterm)[0] - host(bs.cterm)[1]).max() > 1e-9
+
+
+def test_error_codes_not_exceptions_from_c(mods):
+    capi = mods["capi"]
+    lib = capi.load()
+    d = capi.Dims(1, 0, 10, 0, 2)
+    n = C.c_size_t(0)
+    assert lib.scpb200_workspace_bytes(C.byref(d), C.byref(n)) == -1
+    assert b"bad dims" in lib.scpb200_last_error()
+    p = capi.Params()
+    lib.scpb200_default_params(C.byref(p))
+    d = capi.Dims(1, 8, 10, 0, 2)
+    assert lib.scpb200_mpc_setup(C.byref(d), C.byref(p), *([None] * 13)) == -1
