@@ -235,7 +235,8 @@ def test_batch_1024_against_oracle_and_invariants(mods, oracle):
     u_first = u.copy()
     bs.solve()
     assert (host(bs.scp_iters)[conv] <= 2).all()
-    assert np.abs(host(bs.u)[conv] - u_first[conv]).max() < 1e-5
+    # (the SCP stop test is |delta merit| < 1e-3, so a re-solve may still move u by the SCP tolerance)
+    assert np.abs(host(bs.u)[conv] - u_first[conv]).max() < 1e-3
     # subset against the oracle (double precision, same stopping rule), free-running
     idx = np.arange(0, B, 16)
     S = oracle.mpc_setup(cb.x0[idx], cb.u0[idx], cb.veh[idx], cb.poly[idx], Hp=10, dt=0.4)

@@ -1,0 +1,50 @@
+"""Small driver for profiling: a few controller steps of the bench workload at a chosen batch size.
+
+    python tools/run_scp_once.py --batch 148 --steps 2 [--max-scp-iter 1] [--hp 10]
+Prints per-step CUDA-event times of K1 / K4 and the iteration statistics."""
+import argparse
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "senquential-convex-programming-for-trajectory-planning_b200"
+capi = importlib.import_module(PKG + "._capi")
+batch = importlib.import_module(PKG + ".batch")
+scen = importlib.import_module(PKG + ".scenarios")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=148)
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--hp", type=int, default=10)
+ap.add_argument("--max-scp-iter", dest="msi", type=int, default=20)
+ap.add_argument("--step-lo", type=int, default=6)
+ap.add_argument("--step-hi", type=int, default=7)
+ap.add_argument("--assemble", action="store_true")
+args = ap.parse_args()
+
+cb = scen.circle_batch(args.batch, Hp=args.hp, step_lo=args.step_lo, step_hi=args.step_hi)
+p = capi.Params()
+capi.load().scpb200_default_params(C.byref(p))
+p.max_scp_iter = args.msi
+bs = batch.BatchSCP(args.batch, 8, args.hp, params=p)
+bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((args.batch, 8 * args.hp)))
+print("plan", bs.plan())
+for s in range(args.steps):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(); bs.setup(); e[1].record(); bs.solve(); e[2].record()
+    torch.cuda.synchronize()
+    qp, ipm = int(bs.scp_iters.sum()), int(bs.ipm_iters.sum())
+    print(f"step {s}: setup {e[0].elapsed_time(e[1]):.3f} ms, solve {e[1].elapsed_time(e[2]):.3f} ms, QPs {qp}, IPM its {ipm}, "
+          f"max ipm/instance {int(bs.ipm_iters.max())}, us per ipm-iteration-on-critical-path "
+          f"{1e3 * e[1].elapsed_time(e[2]) / max(1, int(bs.ipm_iters.max())):.1f}")
+    bs.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+if args.assemble:
+    out = bs.assemble_dense()
+    torch.cuda.synchronize()
+    print("assembled", out["A"].shape)
