@@ -93,8 +93,8 @@ int scpb200_device_count(void);
 int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes);
 /* same for scpb200_qp_solve_dense on an arbitrary (n1, mc) */
 int scpb200_qp_workspace_bytes(int32_t n1, int32_t mc, size_t *bytes);
-/* launch geometry scpb200_scp_solve would use (diagnostics): out[5] = {grid, threads, dynamic shared bytes,
- * normal matrix in shared memory (1/0), SM count} */
+/* launch geometry scpb200_scp_solve would use (diagnostics): out[6] = {grid, threads, dynamic shared bytes,
+ * normal matrix in shared memory (1/0), SM count, pair-block scratch slots} */
 int scpb200_scp_plan(const scpb200_dims *d, int64_t *out);
 
 /*

@@ -21,7 +21,10 @@ from ._capi import Dims, Params, check
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensors crossing the C ABI must be contiguous"
+    return C.c_void_p(t.data_ptr())
 
 
 class BatchSCP:
@@ -87,10 +90,15 @@ class BatchSCP:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _dev(self, t):
+        """A contiguous float64 device tensor with the same values (NumPy arrays loaded from .npz may be F-ordered)."""
+        return torch.as_tensor(t, dtype=torch.float64).to(self.device).contiguous()
+
     def plan(self):
-        out = (C.c_int64 * 5)()
+        out = (C.c_int64 * 6)()
         check(self.lib.scpb200_scp_plan(C.byref(self.dims), out), "scpb200_scp_plan")
-        return dict(grid=out[0], threads=out[1], smem_bytes=out[2], S_in_shared=bool(out[3]), sms=out[4])
+        return dict(grid=out[0], threads=out[1], smem_bytes=out[2], S_in_shared=bool(out[3]), sms=out[4],
+                    pair_block_scratch_slots=out[5])
 
     def load_inputs(self, x0=None, u0=None, veh=None, poly=None, dsafe=None, dsafe_obst=None, obst=None, u=None):
         """Copy whichever inputs are given (numpy or torch, host or device) into the device buffers."""
@@ -130,7 +138,7 @@ class BatchSCP:
 
     def evaluate(self, u: Optional[torch.Tensor] = None, want_ci: bool = False):
         """QCQP_evaluate (SCP_controller.py:215-265) for the batch at u (default: the current solution)."""
-        u = self.u if u is None else u
+        u = self.u if u is None else self._dev(u)
         f64 = dict(dtype=torch.float64, device=self.device)
         obj, mv, sv = torch.zeros(self.B, **f64), torch.zeros(self.B, **f64), torch.zeros(self.B, **f64)
         feas = torch.zeros(self.B, dtype=torch.int32, device=self.device)
@@ -146,7 +154,7 @@ class BatchSCP:
 
     def assemble_dense(self, ubar: Optional[torch.Tensor] = None):
         """K2: the dense QP (P,q,Aineq,bineq,lb,ub) of SCP_controller.py:93-128 about ubar (default: current u)."""
-        ubar = self.u if ubar is None else ubar
+        ubar = self.u if ubar is None else self._dev(ubar)
         f64 = dict(dtype=torch.float64, device=self.device)
         B, n1, mc = self.B, self.n1, self.mc
         out = dict(P=torch.empty(B, n1, n1, **f64), q=torch.empty(B, n1, **f64), A=torch.empty(B, mc, n1, **f64),
@@ -163,7 +171,7 @@ class BatchSCP:
         self.kernel_launches += 1
 
     def forward_u(self, u: Optional[torch.Tensor] = None):
-        u = self.u if u is None else u
+        u = self.u if u is None else self._dev(u)
         f64 = dict(dtype=torch.float64, device=self.device)
         traj, U = torch.empty(self.B, self.Hp, 2, self.nVeh, **f64), torch.empty(self.B, self.Hp, self.nVeh, **f64)
         with torch.cuda.device(self.device):
@@ -182,6 +190,7 @@ class BatchSCP:
 
     def ode_predict(self, x: torch.Tensor, u_ref: torch.Tensor, T: float, steps: int = 10, nsub: int = 16):
         """Delay-compensation prediction (MPC_Iter.py:25-33) for the batch; returns [B,nVeh,steps,6]."""
+        x, u_ref = self._dev(x), self._dev(u_ref)
         out = torch.empty(self.B, self.nVeh, steps, 6, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.scpb200_ode_predict(C.byref(self.dims), C.byref(self.params), _ptr(x), _ptr(u_ref), _ptr(self.veh),
@@ -204,7 +213,7 @@ def qp_solve_dense(P, q, A, b, lb, ub, params: Optional[Params] = None):
         params = Params()
         lib.scpb200_default_params(C.byref(params))
     f64 = dict(dtype=torch.float64, device=dev)
-    args = [t.contiguous() for t in (P, q, A, b, lb, ub)]
+    args = [t.to(torch.float64).contiguous() for t in (P, q, A, b, lb, ub)]
     x, fval = torch.empty(B, n1, **f64), torch.empty(B, **f64)
     iters, status = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
     zA = torch.empty(B, mc, **f64)

@@ -13,19 +13,20 @@
 // Box rows never enter A: they only add to the diagonal of the normal matrix.  Bounds with
 // |value| >= inf_bound (the omega <= 1e25 row of SCP_controller.py:127) are treated as absent.
 //
-// The normal matrix S lives as a tile-packed lower triangle (8x8 tiles) and is factorised by a blocked
-// right-looking Cholesky: per tile column (a) factor + invert the diagonal tile, (b) panel = panel * Lkk^-T,
-// (c) trailing tiles -= panel panel'.   Triangular solves walk the same tiles and use the stored inverses
-// of the diagonal tiles.
+// The normal matrix S lives as a tile-packed lower triangle (8x8 tiles, layout scp_tphys) and is factorised by a
+// blocked right-looking Cholesky whose factor is then inverted in place (chol_tiles), so that every solve is two
+// triangular mat-vecs.
 //
 // The constraint operator `Op` supplies the problem-specific pieces (structured pair rows for the fused SCP
-// kernel, dense rows for the CVXOPT-replacement entry):
-//     void Op::mul_P(cta, x, y)            y[0..n1) = P x
-//     void Op::add_P(cta, S)               S(lower) += P
-//     void Op::mul_A(cta, x, y)            y[0..mc) = A x
-//     void Op::add_At(cta, w, v)           v[0..n1) += A' w
-//     void Op::add_AtDA(cta, dd, S)        S(lower) += A' diag(dd) A
-// each a sequence of complete phases (entered and left with the CTA synchronised).
+// kernel, dense rows for the CVXOPT-replacement entry).  Products with A and A' are split into a CTA-wide
+// preparation phase and an inline per-row / per-column evaluation, so that the solver can fuse them into its own
+// row and column loops instead of paying a phase (barrier + loop overhead) per product:
+//     void   Op::prep(cta, x, w)                phases; afterwards row_dot refers to x, col_dot to w (either may be null)
+//     double Op::row_dot(r)                     (A x)[r]
+//     double Op::col_dot(c)                     (A' w)[c]
+//     double Op::P_col(c, x)                    (P x)[c]
+//     void   Op::form_normal(cta, m, dd, dg)    S(lower) = P + A' diag(dd) A + diag(dg)      (dg[0..n1): box terms)
+// form_normal must leave the padding of S (rows >= n1) as unit diagonal / zero off-diagonal.
 #pragma once
 #include "scp_common.cuh"
 
@@ -38,12 +39,14 @@ struct IpmCtl {
 // zero padding, the padded diagonal of S is 1.
 struct IpmMem {
     int n1, n1p, T, mc;
-    double *S;      // [T(T+1)/2 * 64]   tile-packed lower triangle of the normal matrix / its Cholesky factor
-    double *Linv;   // [T * 64]          inverses of the diagonal tiles of the factor
+    double *S;      // [T(T+1)/2 * 64]   tile-packed lower triangle of the normal matrix / its Cholesky factor;
+                    //                   chol_tiles leaves X = L^-1 here
     double *x, *q, *rx, *dx, *tn;                    // [n1p]
-    double *bA, *sA, *zA, *rzA, *dsA, *dzA, *ccA;    // [mc]    collision rows
-    double *ub, *sU, *zU, *dsU, *dzU, *ccU;          // [n1p]   x <= ub rows
-    double *lb, *sL, *zL, *dsL, *dzL, *ccL;          // [n1p]   x >= lb rows
+    double *bA, *sA, *zA, *rzA, *dsA, *dzA, *ccA, *eA;   // [mc]    collision rows (e = 1/(s + delta z))
+    double *ub, *sU, *zU, *dsU, *dzU, *ccU, *eU;         // [n1p]   x <= ub rows
+    double *lb, *sL, *zL, *dsL, *dzL, *ccL, *eL;         // [n1p]   x >= lb rows
+    double *dinv;   // [n1p]             reciprocal pivots of the factor
+    double *wbuf;   // [max(T*64, 4*n1p)] tile scratch of the inversion sweep / partial sums of the solves
     double *red;    // [8 * SCP_MAX_WARPS] reduction scratch
     double *t8;     // [16] tile-solve scratch (8) + flags
 };
@@ -53,211 +56,298 @@ struct IpmResult {
     int iters, status;
 };
 
-// ------------------------------------------------------------------------------------------------ 8x8 tile leaf
-// Factor the diagonal tile in place (lower triangle) and write the inverse of the factor to Linv (lower,
-// upper part zero).  Executed by the first 8 threads of the CTA inside a phase (other threads idle).
-// Returns 1 (in *fixed) if a pivot had to be repaired.
-SCP_FN void tile_potrf_inv(int tid, double *Tkk, double *Linv, int *fixed)
+// ------------------------------------------------------------------------------------------------ 8x8 tile leaves
+// All 8x8 tiles (normal matrix, scratch) use the half-row-swapped layout of scp_tphys().
+//
+// Cholesky factor of one diagonal tile, in place (lower triangle; the upper triangle is zeroed), reciprocal
+// pivots to dinv[0..8).  The factorisation is ONE dependent chain of 8 pivots (rsqrt 63 + mul 9 + fma 9 cycles
+// each on B200), so a single lane runs it out of registers with every other update off the chain.
+#define SCP_TRI(r, c) ((r) * ((r) + 1) / 2 + (c))
+SCP_FN void tile_potrf(double *Tkk, double *dinv, int *fixed)
+{
+    double a[36];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[SCP_TRI(r, c)] = Tkk[scp_tphys(r, c)];
+    int bad = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double d = a[SCP_TRI(c, c)];
+        if (!(d > 1e-300)) { d = 1e300; bad = 1; }
+#if SCP_DEVICE_BUILD
+        const double inv = rsqrt(d);
+#else
+        const double inv = 1.0 / sqrt(d);
+#endif
+        dinv[c] = inv;
+        a[SCP_TRI(c, c)] = d * inv;
+#pragma unroll
+        for (int r = c + 1; r < 8; ++r) a[SCP_TRI(r, c)] *= inv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+            for (int r = c2; r < 8; ++r) a[SCP_TRI(r, c2)] -= a[SCP_TRI(r, c)] * a[SCP_TRI(c2, c)];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Tkk[scp_tphys(r, c)] = (c <= r) ? a[SCP_TRI(r, c)] : 0.0;
+    if (bad) *fixed = 1;
+}
+
+// Column j of the inverse of a lower-triangular 8x8 tile L (reciprocal diagonal in dinv), by forward
+// substitution:  X[i][j] = (delta_ij - sum_{k=j}^{i-1} L[i][k] X[k][j]) dinv[i].  The caller stores xcol.
+SCP_FN void tile_trtri_column(const double *L, const double *dinv, int j, double xcol[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < i && k >= j) acc -= L[scp_tphys(i, k)] * xcol[k];
+        xcol[i] = (i >= j) ? acc * dinv[i] : 0.0;
+    }
+}
+
+// ---- warp-level tile products on the FP64 tensor path (DMMA m8n8k4; 37 TFLOP/s measured on B200, the same
+// peak as the DFMA pipe, but two instructions and four 8-byte loads per lane replace ~300 scalar instructions
+// per 8x8x8 product).  Fragment ownership for lane l: A[l>>2][(l&3) + 4h], B[(l&3) + 4h][l>>2],
+// C[l>>2][2(l&3) .. 2(l&3)+1].  The host build (kernel-logic emulator) runs plain loops on lane 0.
+#if SCP_DEVICE_BUILD
+SCP_FN void scp_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+SCP_FN int scp_frag_rowmajor(int lane, int h)     // element (row = lane>>2, col = (lane&3) + 4h)
+{
+    const int r = lane >> 2;
+    return (r << 3) + (((h ^ (r >> 1)) & 1) << 2) + (lane & 3);
+}
+SCP_FN int scp_frag_colmajor(int lane, int h)     // element (row = (lane&3) + 4h, col = lane>>2)
+{
+    return scp_tphys((lane & 3) + 4 * h, lane >> 2);
+}
+SCP_FN int scp_frag_c(int lane)                   // elements (row = lane>>2, cols 2(lane&3), 2(lane&3)+1), 16-byte aligned
+{
+    const int r = lane >> 2, cp = lane & 3;
+    return (r << 3) + ((((cp >> 1) ^ (r >> 1)) & 1) << 2) + ((cp & 1) << 1);
+}
+#endif
+
+// C -= A B'   (A, B, C tiles)
+SCP_FN void warp_tile_syrk(int lane, double *C, const double *A, const double *B)
 {
 #if SCP_DEVICE_BUILD
-    // lanes 0..7 each own one row of the tile in registers; the other lanes of warp 0 shadow lane (tid & 7)
-    // so that the full-mask shuffles stay convergent.
-    if (tid < 32) {
-        const int r = tid & 7;
-        double row[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) row[c] = Tkk[r * 8 + c];
-        double dinv[8];
-        int bad = 0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            double d = __shfl_sync(0xffffffffu, row[c], c);
-            if (!(d > 1e-300)) { d = 1e300; bad = 1; }
-            const double inv = rsqrt(d);
-            dinv[c] = inv;
-            if (r == c) row[c] = d * inv;
-            else if (r > c) row[c] *= inv;
-#pragma unroll
-            for (int c2 = c + 1; c2 < 8; ++c2) {
-                const double l = __shfl_sync(0xffffffffu, row[c], c2);   // L[c2][c]
-                if (r >= c2) row[c2] -= row[c] * l;
-            }
-        }
-        if (tid < 8) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) Tkk[r * 8 + c] = (c <= r) ? row[c] : 0.0;
-        }
-        __syncwarp();
-        // inverse: lane j (< 8) solves L X[:,j] = e_j by forward substitution; L is read back from the tile
-        if (tid < 8) {
-            const int j = tid;
-            double xcol[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double acc = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (k < i && k >= j) acc -= Tkk[i * 8 + k] * xcol[k];
-                xcol[i] = (i >= j) ? acc * dinv[i] : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Linv[i * 8 + j] = xcol[i];
-        }
-        if (tid == 0 && bad) *fixed = 1;
-    }
+    double2 *cp = reinterpret_cast<double2 *>(C + scp_frag_c(lane));
+    const double a0 = A[scp_frag_rowmajor(lane, 0)], a1 = A[scp_frag_rowmajor(lane, 1)];
+    const double b0 = B[scp_frag_rowmajor(lane, 0)], b1 = B[scp_frag_rowmajor(lane, 1)];
+    double2 c = *cp;
+    double n0 = 0.0, n1 = 0.0;
+    scp_dmma(n0, n1, a0, b0);
+    scp_dmma(n0, n1, a1, b1);
+    c.x -= n0; c.y -= n1;
+    *cp = c;
 #else
-    if (tid == 0) {
-        double dinv[8];
-        for (int c = 0; c < 8; ++c) {
-            double d = Tkk[c * 8 + c];
-            if (!(d > 1e-300)) { d = 1e300; *fixed = 1; }
-            const double inv = 1.0 / sqrt(d);
-            dinv[c] = inv;
-            Tkk[c * 8 + c] = d * inv;
-            for (int r = c + 1; r < 8; ++r) Tkk[r * 8 + c] *= inv;
-            for (int c2 = c + 1; c2 < 8; ++c2) {
-                const double l = Tkk[c2 * 8 + c];
-                for (int r = c2; r < 8; ++r) Tkk[r * 8 + c2] -= Tkk[r * 8 + c] * l;
+    if (lane == 0)
+        for (int r = 0; r < 8; ++r)
+            for (int c = 0; c < 8; ++c) {
+                double acc = 0.0;
+                for (int k = 0; k < 8; ++k) acc += A[scp_tphys(r, k)] * B[scp_tphys(c, k)];
+                C[scp_tphys(r, c)] -= acc;
             }
+#endif
+}
+
+// out = sign * sum_{j < nprod} A_j B_j   with A_j = Abase + j*astride, B_j = Bbase + j*bstride (plain products)
+SCP_FN void warp_tile_gemm_sum(int lane, double *out, const double *Abase, int astride, const double *Bbase, int bstride,
+                               int nprod, double sign)
+{
+#if SCP_DEVICE_BUILD
+    double n0 = 0.0, n1 = 0.0;
+    const int ia0 = scp_frag_rowmajor(lane, 0), ia1 = scp_frag_rowmajor(lane, 1);
+    const int ib0 = scp_frag_colmajor(lane, 0), ib1 = scp_frag_colmajor(lane, 1);
+    for (int j = 0; j < nprod; ++j) {
+        const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
+        const double a0 = A[ia0], a1 = A[ia1], b0 = B[ib0], b1 = B[ib1];
+        scp_dmma(n0, n1, a0, b0);
+        scp_dmma(n0, n1, a1, b1);
+    }
+    double2 c;
+    c.x = sign * n0; c.y = sign * n1;
+    *reinterpret_cast<double2 *>(out + scp_frag_c(lane)) = c;
+#else
+    if (lane == 0) {
+        double acc[64];
+        for (int e = 0; e < 64; ++e) acc[e] = 0.0;
+        for (int j = 0; j < nprod; ++j) {
+            const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c)
+                    for (int k = 0; k < 8; ++k) acc[r * 8 + c] += A[scp_tphys(r, k)] * B[scp_tphys(k, c)];
         }
         for (int r = 0; r < 8; ++r)
-            for (int c = r + 1; c < 8; ++c) Tkk[r * 8 + c] = 0.0;
-        for (int j = 0; j < 8; ++j) {
-            double xcol[8];
-            for (int i = 0; i < 8; ++i) {
-                double acc = (i == j) ? 1.0 : 0.0;
-                for (int k = j; k < i; ++k) acc -= Tkk[i * 8 + k] * xcol[k];
-                xcol[i] = (i >= j) ? acc * dinv[i] : 0.0;
-            }
-            for (int i = 0; i < 8; ++i) Linv[i * 8 + j] = xcol[i];
-        }
+            for (int c = 0; c < 8; ++c) out[scp_tphys(r, c)] = sign * acc[r * 8 + c];
     }
 #endif
 }
 
 // ------------------------------------------------------------------------------------------------ Cholesky
-// In-place blocked Cholesky of the tile-packed lower triangle.  *fixed is set if any pivot was repaired.
-SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed)
+// In-place blocked right-looking Cholesky of the tile-packed lower triangle, followed by the in-place
+// inversion of the factor: on exit m.S holds X = L^-1 (lower triangular, tile-packed).
+//
+// Why the inverse: forward/backward substitution is a dependent chain over the n1 unknowns (two synchronised
+// steps per tile column, ~13k cycles per solve at n1 = 81 on B200) and the interior-point iteration needs two
+// solves per factorisation, one after the other.  With X every solve is two triangular mat-vecs
+// (S^-1 b = X'(X b)); the inversion costs n1^3/6 multiply-adds once per factorisation on the tensor path.
+//   per tile column K:  (a) lane 0 factors the diagonal tile, (b) panel rows are solved against it by
+//   substitution (one thread per row), (c) trailing tiles -= panel panel' (one warp per tile, DMMA).
+//   then:               (d) all diagonal tiles are inverted in one phase (one thread per tile column),
+//                       (e) for K = T-2 .. 0:  W = L[K+1:,K] X_KK ;  X[K+1:,K] = -X[K+1:,K+1:] W   (DMMA).
+// *fixed is set if any pivot had to be repaired.
+SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
 {
     const int T = m.T;
-    double *S = m.S;
+    double *S = m.S, *dinv = m.dinv, *wbuf = m.wbuf;
     for (int K = 0; K < T; ++K) {
-        double *Skk = S + scp_tile_off(K, K);
-        double *Lki = m.Linv + K * SCP_TILE2;
+        double *Lkk = S + scp_tile_off(K, K);
         CTA_PHASE(tid)
-            tile_potrf_inv(tid, Skk, Lki, fixed);
+            if (tid == 0) tile_potrf(Lkk, dinv + K * 8, fixed);
         CTA_PHASE_END
+        SCP_TIMER(2)
         const int Tr = T - K - 1;
         if (Tr == 0) break;
-        // (b) panel rows: L_IK[r][:] = S_IK[r][:] * Lkk^-T       one thread per panel row
+        // (b) panel rows: x L_KK' = s  ->  x[c] = (s[c] - sum_{c2<c} x[c2] L[c][c2]) dinv[c]
         CTA_PHASE(tid)
             for (int pr = tid; pr < Tr * 8; pr += cta.nt) {
                 const int I = K + 1 + (pr >> 3), r = pr & 7;
-                double *row = S + scp_tile_off(I, K) + r * 8;
-                double s[8], o[8];
+                double *row = S + scp_tile_off(I, K) + (r << 3);
+                const int h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;       // where logical columns 0-3 / 4-7 live
+                double x[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) s[c] = row[c];
+                for (int c = 0; c < 4; ++c) { x[c] = row[h0 + c]; x[c + 4] = row[h1 + c]; }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double acc = 0.0;
+                    double acc = x[c];
 #pragma unroll
                     for (int c2 = 0; c2 < 8; ++c2)
-                        if (c2 <= c) acc += s[c2] * Lki[c * 8 + c2];
-                    o[c] = acc;
+                        if (c2 < c) acc -= x[c2] * Lkk[scp_tphys(c, c2)];
+                    x[c] = acc * dinv[K * 8 + c];
                 }
 #pragma unroll
-                for (int c = 0; c < 8; ++c) row[c] = o[c];
+                for (int c = 0; c < 4; ++c) { row[h0 + c] = x[c]; row[h1 + c] = x[c + 4]; }
             }
         CTA_PHASE_END
-        // (c) trailing update: S_IJ -= L_IK L_JK'   (K < J <= I), a 4x4 quadrant per thread
-        CTA_PHASE(tid)
-            const int ntask = (Tr * (Tr + 1) >> 1) * 4;
-            for (int t = tid; t < ntask; t += cta.nt) {
-                int ii, jj;
-                scp_tri_decode(t >> 2, &ii, &jj);
-                const int I = K + 1 + ii, J = K + 1 + jj;
-                const int r0 = (t & 2) ? 4 : 0, c0 = (t & 1) ? 4 : 0;
-                const double *Ai = S + scp_tile_off(I, K) + r0 * 8;
-                const double *Bj = S + scp_tile_off(J, K) + c0 * 8;
-                double *C = S + scp_tile_off(I, J) + r0 * 8 + c0;
-                double acc[4][4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { a[r] = Ai[r * 8 + k]; b[r] = Bj[r * 8 + k]; }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[r][c] += a[r] * b[c];
+        SCP_TIMER(3)
+        // (c) trailing update: S_IJ -= L_IK L_JK'   (K < J <= I), one warp per output tile
+        WARP_SECTION(w, nw)
+            WARP_PHASE(lane)
+                const int ntile = Tr * (Tr + 1) >> 1;
+                for (int t = w; t < ntile; t += nw) {
+                    int ii, jj;
+                    scp_tri_decode(t, &ii, &jj);
+                    warp_tile_syrk(lane, S + scp_tile_off(K + 1 + ii, K + 1 + jj), S + scp_tile_off(K + 1 + ii, K),
+                                   S + scp_tile_off(K + 1 + jj, K));
                 }
+            WARP_PHASE_END
+        WARP_SECTION_END
+        CTA_SYNC
+        SCP_TIMER(4)
+    }
+    // (d) invert every diagonal tile: thread (K, j) computes column j of inv(L_KK) in registers ...
+    CTA_PHASE(tid)
+        for (int t0 = 0; t0 < T * 8; t0 += cta.nt) {
+            const int t = t0 + tid;
+            if (t < T * 8) {
+                const int K = t >> 3, j = t & 7;
+                double xcol[8];
+                tile_trtri_column(S + scp_tile_off(K, K), dinv + K * 8, j, xcol);
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) C[r * 8 + c] -= acc[r][c];
+                for (int i = 0; i < 8; ++i) wbuf[K * 64 + (i << 3) + ((((j >> 2) ^ (i >> 1)) & 1) << 2) + (j & 3)] = xcol[i];
             }
-        CTA_PHASE_END
+        }
+    CTA_PHASE_END
+    // ... and the tiles are replaced once every column has been read
+    CTA_PHASE(tid)
+        for (int e = tid; e < T * 64; e += cta.nt) S[scp_tile_off(e >> 6, e >> 6) + (e & 63)] = wbuf[e];
+    CTA_PHASE_END
+    SCP_TIMER(5)
+    // (e) off-diagonal tiles of the inverse, column by column from the right
+    for (int K = T - 2; K >= 0; --K) {
+        const int Tr = T - K - 1;
+        // W_I = L_IK X_KK   (I > K), one warp per panel tile
+        WARP_SECTION(w, nw)
+            WARP_PHASE(lane)
+                for (int ii = w; ii < Tr; ii += nw)
+                    warp_tile_gemm_sum(lane, wbuf + ii * 64, S + scp_tile_off(K + 1 + ii, K), 0, S + scp_tile_off(K, K), 0, 1, 1.0);
+            WARP_PHASE_END
+        WARP_SECTION_END
+        CTA_SYNC
+        SCP_TIMER(6)
+        // X_IK = -sum_{J=K+1..I} X_IJ W_J.  Tile rows are paired (I, T+K-I) so that every warp carries the same
+        // number of tile products.
+        WARP_SECTION(w, nw)
+            WARP_PHASE(lane)
+                const int ngroup = (Tr + 1) >> 1;
+                for (int grp = w; grp < ngroup; grp += nw)
+                    for (int half = 0; half < 2; ++half) {
+                        const int ii = half == 0 ? grp : Tr - 1 - grp;          // 0-based tile row below K
+                        if (half == 1 && ii == grp) break;                        // odd Tr: the middle row once
+                        const int I = K + 1 + ii;
+                        warp_tile_gemm_sum(lane, S + scp_tile_off(I, K), S + scp_tile_off(I, K + 1), SCP_TILE2, wbuf, SCP_TILE2,
+                                           ii + 1, -1.0);
+                    }
+            WARP_PHASE_END
+        WARP_SECTION_END
+        CTA_SYNC
+        SCP_TIMER(7)
     }
 }
 
-// v := S^-1 v  using the factor in m.S / m.Linv (v has length n1p)
-SCP_FN void chol_solve_tiles(Cta &cta, const IpmMem &m, double *v)
+// v := S^-1 v = X'(X v) with X = L^-1 left in m.S by chol_tiles (v has length n1p; `tmp` is n1p scratch).
+// One thread per row (then per column) of X, four accumulators each.
+SCP_FN void chol_solve_tiles(Cta &cta, const IpmMem &m, double *v, double *tmp)
 {
-    const int T = m.T;
+    const int T = m.T, n1p = m.n1p;
     const double *S = m.S;
-    double *t8 = m.t8;
-    for (int K = 0; K < T; ++K) {                       // forward: L y = v
-        const double *Lki = m.Linv + K * SCP_TILE2;
-        CTA_PHASE(tid)
-            if (tid < 8) {
-                double acc = 0.0;
-                for (int c = 0; c <= tid; ++c) acc += Lki[tid * 8 + c] * v[K * 8 + c];
-                t8[tid] = acc;
+    CTA_PHASE(tid)                                  // tmp = X v
+        for (int i = tid; i < n1p; i += cta.nt) {
+            const int I = i >> 3, r = i & 7, h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int J = 0; J <= I; ++J) {
+                const double *row = S + scp_tile_off(I, J) + (r << 3);
+                const double *vj = v + J * 8;
+                a0 += row[h0] * vj[0] + row[h0 + 1] * vj[1];
+                a1 += row[h0 + 2] * vj[2] + row[h0 + 3] * vj[3];
+                a2 += row[h1] * vj[4] + row[h1 + 1] * vj[5];
+                a3 += row[h1 + 2] * vj[6] + row[h1 + 3] * vj[7];
             }
-        CTA_PHASE_END
-        CTA_PHASE(tid)
-            if (tid < 8) v[K * 8 + tid] = t8[tid];
-            for (int pr = tid; pr < (T - K - 1) * 8; pr += cta.nt) {
-                const int I = K + 1 + (pr >> 3), r = pr & 7;
-                const double *row = S + scp_tile_off(I, K) + r * 8;
-                double acc = 0.0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc += row[c] * t8[c];
-                v[I * 8 + r] -= acc;
+            tmp[i] = (a0 + a1) + (a2 + a3);
+        }
+    CTA_PHASE_END
+    CTA_PHASE(tid)                                  // v = X' tmp
+        for (int j = tid; j < n1p; j += cta.nt) {
+            const int J = j >> 3, c = j & 7, lo = c & 3, he = (c >> 2) << 2, ho = he ^ 4;   // rows 0,1,4,5 / rows 2,3,6,7
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int I = J; I < T; ++I) {
+                const double *tl = S + scp_tile_off(I, J);
+                const double *ti = tmp + I * 8;
+                a0 += tl[he + lo] * ti[0] + tl[8 + he + lo] * ti[1];
+                a1 += tl[16 + ho + lo] * ti[2] + tl[24 + ho + lo] * ti[3];
+                a2 += tl[32 + he + lo] * ti[4] + tl[40 + he + lo] * ti[5];
+                a3 += tl[48 + ho + lo] * ti[6] + tl[56 + ho + lo] * ti[7];
             }
-        CTA_PHASE_END
-    }
-    for (int K = T - 1; K >= 0; --K) {                  // backward: L' x = y
-        const double *Lki = m.Linv + K * SCP_TILE2;
-        CTA_PHASE(tid)
-            if (tid < 8) {
-                double acc = 0.0;
-                for (int r = tid; r < 8; ++r) acc += Lki[r * 8 + tid] * v[K * 8 + r];
-                t8[tid] = acc;
-            }
-        CTA_PHASE_END
-        CTA_PHASE(tid)
-            if (tid < 8) v[K * 8 + tid] = t8[tid];
-            for (int j = tid; j < K * 8; j += cta.nt) {
-                const double *col = S + scp_tile_off(K, j >> 3) + (j & 7);
-                double acc = 0.0;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) acc += col[r * 8] * t8[r];
-                v[j] -= acc;
-            }
-        CTA_PHASE_END
-    }
+            v[j] = (a0 + a1) + (a2 + a3);
+        }
+    CTA_PHASE_END
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
 SCP_FN bool ipm_has_ub(const IpmMem &m, const IpmCtl &ctl, int c) { return c < m.n1 && fabs(m.ub[c]) < ctl.inf_bound; }
 SCP_FN bool ipm_has_lb(const IpmMem &m, const IpmCtl &ctl, int c) { return c < m.n1 && fabs(m.lb[c]) < ctl.inf_bound; }
 
-// S := 0 with unit diagonal on the padding; then the caller adds P, A'DA and the box diagonal
+// S := 0 with unit diagonal on the padding (helper for operators that accumulate into S)
 SCP_FN void ipm_clear_S(Cta &cta, const IpmMem &m)
 {
     CTA_PHASE(tid)
@@ -270,6 +360,11 @@ SCP_FN void ipm_clear_S(Cta &cta, const IpmMem &m)
 }
 
 // ------------------------------------------------------------------------------------------------ the solver
+// Per-row arithmetic of one direction computation, shared by collision and box rows.  With
+//     e = 1/(s + delta z),  dd = z e  (= 1/(s/z + delta)),  bs = -s z + sigma mu - cc
+// the regularised Newton system gives  w1 = dd rz + bs e,  dz = w1 + dd (G dx),  ds = (bs - s dz)/z.
+SCP_FN double ipm_w1(double s, double z, double rz, double e, double bs) { return z * e * rz + bs * e; }
+
 // On entry m.q, m.bA, m.ub, m.lb hold the problem data (padding of q/ub/lb beyond n1 is ignored).
 // On exit m.x holds the solution.
 template <class Op>
@@ -277,6 +372,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
 {
     const int n1 = m.n1, n1p = m.n1p, mc = m.mc;
     double *red = m.red;
+    SCP_TIMER_DECL
     int *fixed_p = (int *)(m.t8 + 8);   // pivot-repair flag lives in shared scratch (t8 has 16 slots, 8 used)
 
     // ---- constants: row count, residual scales, zero the padding ---------------------------------
@@ -300,27 +396,36 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
     const double resz0 = fmax(1.0, sqrt(cta_red_sum(cta, red, 2)));
 
     // ---- starting point (coneqp): (P + G'G) x = G'h - q ; z = Gx - h ; s = -z ; shift ------------
-    ipm_clear_S(cta, m);
-    op.add_P(cta, m.S);
     CTA_PHASE(tid)
         for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = 1.0;            // dd = 1
         for (int c = tid; c < n1p; c += cta.nt) {
-            double d = 0.0, rhs = 0.0;
-            if (ipm_has_ub(m, ctl, c)) { d += 1.0; rhs += m.ub[c]; }
-            if (ipm_has_lb(m, ctl, c)) { d += 1.0; rhs += m.lb[c]; }
-            if (c < n1) { m.S[scp_sidx(c, c)] += d; m.x[c] = rhs - m.q[c]; }
+            double d = 0.0;
+            if (ipm_has_ub(m, ctl, c)) d += 1.0;
+            if (ipm_has_lb(m, ctl, c)) d += 1.0;
+            m.tn[c] = d;                                                   // box part of the diagonal
         }
     CTA_PHASE_END
-    op.add_AtDA(cta, m.dsA, m.S);
-    op.add_At(cta, m.bA, m.x);
-    chol_tiles(cta, m, fixed_p);
-    chol_solve_tiles(cta, m, m.x);
-    op.mul_A(cta, m.x, m.rzA);                                              // rzA = A x (scratch)
+    SCP_TIMER(0)
+    op.form_normal(cta, m, m.dsA, m.tn);
+    op.prep(cta, (const double *)0, m.bA);
+    CTA_PHASE(tid)
+        for (int c = tid; c < n1; c += cta.nt) {
+            double rhs = op.col_dot(c) - m.q[c];
+            if (ipm_has_ub(m, ctl, c)) rhs += m.ub[c];
+            if (ipm_has_lb(m, ctl, c)) rhs += m.lb[c];
+            m.x[c] = rhs;
+        }
+    CTA_PHASE_END
+    SCP_TIMER(1)
+    chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
+    chol_solve_tiles(cta, m, m.x, m.tn);
+    SCP_TIMER(8)
+    op.prep(cta, m.x, (const double *)0);
     CTA_RED_BEGIN(cta, 3)
     CTA_PHASE(tid)
         double nrm = 0.0, ts = -1e300, tz = -1e300;
         for (int r = tid; r < mc; r += cta.nt) {
-            const double z = m.rzA[r] - m.bA[r];
+            const double z = op.row_dot(r) - m.bA[r];
             m.zA[r] = z; m.sA[r] = -z;
             nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
         }
@@ -338,67 +443,69 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         CTA_RED_MAX(cta, red, 1, tid, ts)
         CTA_RED_MAX(cta, red, 2, tid, tz)
     CTA_PHASE_END_RED(cta, red, 3)
+    double as_shift, az_shift;
     {
         const double nrm = sqrt(cta_red_sum(cta, red, 0));
         const double ts = cta_red_max(cta, red, 1), tz = cta_red_max(cta, red, 2);
         const double thr = -1e-8 * fmax(nrm, 1.0);
-        const double as = (ts >= thr) ? 1.0 + ts : 0.0, az = (tz >= thr) ? 1.0 + tz : 0.0;
-        CTA_PHASE(tid)
-            for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += as; m.zA[r] += az; }
-            for (int c = tid; c < n1p; c += cta.nt) {
-                if (ipm_has_ub(m, ctl, c)) { m.sU[c] += as; m.zU[c] += az; }
-                if (ipm_has_lb(m, ctl, c)) { m.sL[c] += as; m.zL[c] += az; }
-            }
-        CTA_PHASE_END
+        as_shift = (ts >= thr) ? 1.0 + ts : 0.0;
+        az_shift = (tz >= thr) ? 1.0 + tz : 0.0;
     }
+    CTA_PHASE(tid)
+        for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += as_shift; m.zA[r] += az_shift; }
+        for (int c = tid; c < n1p; c += cta.nt) {
+            if (ipm_has_ub(m, ctl, c)) { m.sU[c] += as_shift; m.zU[c] += az_shift; }
+            if (ipm_has_lb(m, ctl, c)) { m.sL[c] += as_shift; m.zL[c] += az_shift; }
+        }
+    CTA_PHASE_END
 
     int iters = 0, status = SCPB200_ST_QP_MAXITER;
     double f0 = 0.0, gap = 0.0, relgap = -1.0, pres = 0.0, dres = 0.0;
     for (iters = 0; iters <= ctl.max_iter; ++iters) {
-        // ---- residuals: rx = Px + q + G'z ; rz = s + Gx - h ; costs --------------------------------
-        op.mul_P(cta, m.x, m.tn);                                            // tn = P x
-        op.mul_A(cta, m.x, m.rzA);                                           // rzA = A x
-        CTA_RED_BEGIN(cta, 4)
+        // ---- residuals: rx = Px + q + G'z ; rz = s + Gx - h ; costs; e = 1/(s + delta z) -----------
+        SCP_TIMER(0)
+        op.prep(cta, m.x, m.zA);
+        CTA_RED_BEGIN(cta, 5)
         CTA_PHASE(tid)
-            double pf = 0.0, pg = 0.0, prz = 0.0, pzr = 0.0;
+            double pf = 0.0, pg = 0.0, prz = 0.0, pzr = 0.0, prx = 0.0;
             for (int c = tid; c < n1p; c += cta.nt) {
                 double r = 0.0;
                 if (c < n1) {
-                    pf += m.x[c] * (0.5 * m.tn[c] + m.q[c]);
-                    r = m.tn[c] + m.q[c];
+                    const double px = op.P_col(c, m.x);
+                    pf += m.x[c] * (0.5 * px + m.q[c]);
+                    r = px + m.q[c] + op.col_dot(c);
                 }
                 if (ipm_has_ub(m, ctl, c)) {
-                    const double rz = m.sU[c] + m.x[c] - m.ub[c];
-                    r += m.zU[c]; pg += m.sU[c] * m.zU[c]; prz += rz * rz; pzr += m.zU[c] * rz;
+                    const double s = m.sU[c], z = m.zU[c], rz = s + m.x[c] - m.ub[c];
+                    r += z; pg += s * z; prz += rz * rz; pzr += z * rz;
+                    m.eU[c] = 1.0 / (s + ctl.dual_reg * z);
                 }
                 if (ipm_has_lb(m, ctl, c)) {
-                    const double rz = m.sL[c] - m.x[c] + m.lb[c];
-                    r -= m.zL[c]; pg += m.sL[c] * m.zL[c]; prz += rz * rz; pzr += m.zL[c] * rz;
+                    const double s = m.sL[c], z = m.zL[c], rz = s - m.x[c] + m.lb[c];
+                    r -= z; pg += s * z; prz += rz * rz; pzr += z * rz;
+                    m.eL[c] = 1.0 / (s + ctl.dual_reg * z);
                 }
                 m.rx[c] = r;
+                prx += r * r;
             }
             for (int r = tid; r < mc; r += cta.nt) {
-                const double rz = m.sA[r] + m.rzA[r] - m.bA[r];
+                const double s = m.sA[r], z = m.zA[r];
+                const double rz = s + op.row_dot(r) - m.bA[r];
                 m.rzA[r] = rz;
-                pg += m.sA[r] * m.zA[r]; prz += rz * rz; pzr += m.zA[r] * rz;
+                pg += s * z; prz += rz * rz; pzr += z * rz;
+                m.eA[r] = 1.0 / (s + ctl.dual_reg * z);
             }
             CTA_RED_SUM(cta, red, 0, tid, pf)
             CTA_RED_SUM(cta, red, 1, tid, pg)
             CTA_RED_SUM(cta, red, 2, tid, prz)
             CTA_RED_SUM(cta, red, 3, tid, pzr)
-        CTA_PHASE_END_RED(cta, red, 4)
+            CTA_RED_SUM(cta, red, 4, tid, prx)
+        CTA_PHASE_END_RED(cta, red, 5)
         f0 = cta_red_sum(cta, red, 0);
         gap = cta_red_sum(cta, red, 1);
         const double resz = sqrt(cta_red_sum(cta, red, 2));
         const double zrz = cta_red_sum(cta, red, 3);
-        op.add_At(cta, m.zA, m.rx);                                          // rx += A' zA
-        CTA_RED_BEGIN(cta, 1)
-        CTA_PHASE(tid)
-            double p = 0.0;
-            for (int c = tid; c < n1; c += cta.nt) p += m.rx[c] * m.rx[c];
-            CTA_RED_SUM(cta, red, 0, tid, p)
-        CTA_PHASE_END_RED(cta, red, 1)
-        const double resx = sqrt(cta_red_sum(cta, red, 0));
+        const double resx = sqrt(cta_red_sum(cta, red, 4));
         const double dcost = f0 + zrz - gap;
         if (f0 < 0.0) relgap = gap / -f0;
         else if (dcost > 0.0) relgap = gap / dcost;
@@ -408,91 +515,97 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         if (pres <= ctl.feastol && dres <= ctl.feastol &&
             (gap <= ctl.abstol || (relgap >= 0.0 && relgap <= ctl.reltol))) { status = 0; break; }
         if (iters == ctl.max_iter) break;
+        SCP_TIMER(9)
 
-        // ---- normal matrix with D = 1/(s/z + delta) and its factor ---------------------------------
-        ipm_clear_S(cta, m);
-        op.add_P(cta, m.S);
+        // ---- normal matrix with dd = z e and its inverted factor -----------------------------------
         CTA_PHASE(tid)
-            for (int r = tid; r < mc; r += cta.nt) m.dzA[r] = 1.0 / (m.sA[r] / m.zA[r] + ctl.dual_reg);   // dd in dzA
-            for (int c = tid; c < n1; c += cta.nt) {
+            for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = m.zA[r] * m.eA[r];          // dd in dsA
+            for (int c = tid; c < n1p; c += cta.nt) {
                 double d = 0.0;
-                if (ipm_has_ub(m, ctl, c)) d += 1.0 / (m.sU[c] / m.zU[c] + ctl.dual_reg);
-                if (ipm_has_lb(m, ctl, c)) d += 1.0 / (m.sL[c] / m.zL[c] + ctl.dual_reg);
-                m.S[scp_sidx(c, c)] += d;
+                if (ipm_has_ub(m, ctl, c)) d += m.zU[c] * m.eU[c];
+                if (ipm_has_lb(m, ctl, c)) d += m.zL[c] * m.eL[c];
+                m.tn[c] = d;
             }
         CTA_PHASE_END
-        op.add_AtDA(cta, m.dzA, m.S);
-        chol_tiles(cta, m, fixed_p);
+        op.form_normal(cta, m, m.dsA, m.tn);
+        SCP_TIMER(1)
+        chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
 
         const double mu = gap / mrows;
         double sigma = 0.0, step = 1.0;
         for (int pass = 0; pass < 2; ++pass) {
-            // w1 = D (rz + bs/z), bs = -s z + sigma mu - [pass 1] (ds_a dz_a);  rhs = -rx - G'w1
+            const double smu = sigma * mu;
+            // w1 for the collision rows (input of A'w1); bs = -s z + sigma mu - [pass 1] (ds_a dz_a)
             CTA_PHASE(tid)
                 for (int r = tid; r < mc; r += cta.nt) {
                     const double s = m.sA[r], z = m.zA[r];
-                    double bs = -s * z + sigma * mu;
+                    double bs = smu - s * z;
                     if (pass == 1) bs -= m.ccA[r];
-                    m.dzA[r] = (m.rzA[r] + bs / z) / (s / z + ctl.dual_reg);          // w1 in dzA
+                    m.dzA[r] = ipm_w1(s, z, m.rzA[r], m.eA[r], bs);                       // w1 in dzA
                 }
+            CTA_PHASE_END
+            op.prep(cta, (const double *)0, m.dzA);
+            // rhs = -rx - G'w1
+            CTA_PHASE(tid)
                 for (int c = tid; c < n1p; c += cta.nt) {
-                    double rhs = -m.rx[c];
+                    double rhs = 0.0;
+                    if (c < n1) rhs = -m.rx[c] - op.col_dot(c);
                     if (ipm_has_ub(m, ctl, c)) {
                         const double s = m.sU[c], z = m.zU[c];
-                        double bs = -s * z + sigma * mu;
+                        double bs = smu - s * z;
                         if (pass == 1) bs -= m.ccU[c];
-                        const double w1 = (s + m.x[c] - m.ub[c] + bs / z) / (s / z + ctl.dual_reg);
+                        const double w1 = ipm_w1(s, z, s + m.x[c] - m.ub[c], m.eU[c], bs);
                         m.dzU[c] = w1; rhs -= w1;
                     }
                     if (ipm_has_lb(m, ctl, c)) {
                         const double s = m.sL[c], z = m.zL[c];
-                        double bs = -s * z + sigma * mu;
+                        double bs = smu - s * z;
                         if (pass == 1) bs -= m.ccL[c];
-                        const double w1 = (s - m.x[c] + m.lb[c] + bs / z) / (s / z + ctl.dual_reg);
+                        const double w1 = ipm_w1(s, z, s - m.x[c] + m.lb[c], m.eL[c], bs);
                         m.dzL[c] = w1; rhs += w1;
                     }
-                    m.dx[c] = (c < n1) ? rhs : 0.0;
-                    m.tn[c] = 0.0;
+                    m.dx[c] = rhs;
                 }
             CTA_PHASE_END
-            op.add_At(cta, m.dzA, m.tn);                                     // tn = A' w1A
-            CTA_PHASE(tid)
-                for (int c = tid; c < n1; c += cta.nt) m.dx[c] -= m.tn[c];
-            CTA_PHASE_END
-            chol_solve_tiles(cta, m, m.dx);
-            op.mul_A(cta, m.dx, m.dsA);                                      // dsA = A dx (scratch)
+            SCP_TIMER(10)
+            chol_solve_tiles(cta, m, m.dx, m.tn);
+            SCP_TIMER(8)
+            op.prep(cta, m.dx, (const double *)0);
             CTA_RED_BEGIN(cta, 3)
             CTA_PHASE(tid)
                 double pdd = 0.0, ts = 0.0, tz = 0.0;
                 for (int r = tid; r < mc; r += cta.nt) {
                     const double s = m.sA[r], z = m.zA[r];
-                    double bs = -s * z + sigma * mu;
+                    double bs = smu - s * z;
                     if (pass == 1) bs -= m.ccA[r];
-                    const double dz = m.dzA[r] + m.dsA[r] / (s / z + ctl.dual_reg);
-                    const double ds = (bs - s * dz) / z;
+                    const double pinv = 1.0 / (s * z);                                    // 1/z = pinv s, 1/s = pinv z
+                    const double dz = m.dzA[r] + z * m.eA[r] * op.row_dot(r);
+                    const double ds = (bs - s * dz) * (pinv * s);
                     m.dzA[r] = dz; m.dsA[r] = ds;
-                    pdd += ds * dz; ts = fmax(ts, -ds / s); tz = fmax(tz, -dz / z);
+                    pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
                     if (pass == 0) m.ccA[r] = ds * dz;
                 }
                 for (int c = tid; c < n1p; c += cta.nt) {
                     if (ipm_has_ub(m, ctl, c)) {
                         const double s = m.sU[c], z = m.zU[c];
-                        double bs = -s * z + sigma * mu;
+                        double bs = smu - s * z;
                         if (pass == 1) bs -= m.ccU[c];
-                        const double dz = m.dzU[c] + m.dx[c] / (s / z + ctl.dual_reg);
-                        const double ds = (bs - s * dz) / z;
+                        const double pinv = 1.0 / (s * z);
+                        const double dz = m.dzU[c] + z * m.eU[c] * m.dx[c];
+                        const double ds = (bs - s * dz) * (pinv * s);
                         m.dzU[c] = dz; m.dsU[c] = ds;
-                        pdd += ds * dz; ts = fmax(ts, -ds / s); tz = fmax(tz, -dz / z);
+                        pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
                         if (pass == 0) m.ccU[c] = ds * dz;
                     }
                     if (ipm_has_lb(m, ctl, c)) {
                         const double s = m.sL[c], z = m.zL[c];
-                        double bs = -s * z + sigma * mu;
+                        double bs = smu - s * z;
                         if (pass == 1) bs -= m.ccL[c];
-                        const double dz = m.dzL[c] - m.dx[c] / (s / z + ctl.dual_reg);
-                        const double ds = (bs - s * dz) / z;
+                        const double pinv = 1.0 / (s * z);
+                        const double dz = m.dzL[c] - z * m.eL[c] * m.dx[c];
+                        const double ds = (bs - s * dz) * (pinv * s);
                         m.dzL[c] = dz; m.dsL[c] = ds;
-                        pdd += ds * dz; ts = fmax(ts, -ds / s); tz = fmax(tz, -dz / z);
+                        pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
                         if (pass == 0) m.ccL[c] = ds * dz;
                     }
                 }
@@ -508,6 +621,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                 const double base = fmin(1.0, fmax(0.0, 1.0 - step + dsdz / gap * step * step));
                 sigma = base * base * base;
             }
+            SCP_TIMER(11)
         }
         CTA_PHASE(tid)
             for (int c = tid; c < n1p; c += cta.nt) {

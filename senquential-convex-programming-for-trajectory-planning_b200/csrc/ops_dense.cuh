@@ -10,15 +10,47 @@ struct DenseOp {
     const double *P;   // [n1][n1]  (global)
     const double *A;   // [mc][n1]  (global)
 
-    SCP_MFN void mul_P(Cta &cta, const double *x, double *y) const
+    const double *xp, *wp;   // the x / w of the last prep
+
+    SCP_MFN double P_col(int c, const double *x) const
+    {
+        double acc = 0.0;
+        for (int j = 0; j < n1; ++j) acc += P[(size_t)j * n1 + c] * x[j];          // P symmetric: column walk is coalesced
+        return acc;
+    }
+    SCP_MFN void prep(Cta &cta, const double *x, const double *w)
+    {
+        (void)cta;
+        xp = x;
+        wp = w;
+    }
+    SCP_MFN double row_dot(int r) const
+    {
+        const double *Ar = A + (size_t)r * n1;
+        double acc = 0.0;
+        for (int c = 0; c < n1; ++c) acc += Ar[c] * xp[c];
+        return acc;
+    }
+    SCP_MFN double col_dot(int c) const
+    {
+        double acc = 0.0;
+        for (int r = 0; r < mc; ++r) acc += A[(size_t)r * n1 + c] * wp[r];
+        return acc;
+    }
+
+    // S(lower) = P + A' diag(dd) A + diag(dg): clear, then accumulate
+    template <class Mem>
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg)
     {
         CTA_PHASE(tid)
-            for (int c = tid; c < n1; c += cta.nt) {
-                double acc = 0.0;
-                for (int j = 0; j < n1; ++j) acc += P[(size_t)j * n1 + c] * x[j];   // P symmetric: column walk is coalesced
-                y[c] = acc;
-            }
+            const int tot = (m.T * (m.T + 1) >> 1) * SCP_TILE2;
+            for (int e = tid; e < tot; e += cta.nt) m.S[e] = 0.0;
         CTA_PHASE_END
+        CTA_PHASE(tid)
+            for (int c = tid; c < m.n1p; c += cta.nt) m.S[scp_sidx(c, c)] = c < n1 ? dg[c] : 1.0;
+        CTA_PHASE_END
+        add_P(cta, m.S);
+        add_AtDA(cta, dd, m.S);
     }
 
     SCP_MFN void add_P(Cta &cta, double *S) const
@@ -29,29 +61,6 @@ struct DenseOp {
                 int ci, cj;
                 scp_tri_decode(e, &ci, &cj);
                 S[scp_sidx(ci, cj)] += 0.5 * (P[(size_t)ci * n1 + cj] + P[(size_t)cj * n1 + ci]);
-            }
-        CTA_PHASE_END
-    }
-
-    SCP_MFN void mul_A(Cta &cta, const double *x, double *y) const
-    {
-        CTA_PHASE(tid)
-            for (int r = tid; r < mc; r += cta.nt) {
-                const double *Ar = A + (size_t)r * n1;
-                double acc = 0.0;
-                for (int c = 0; c < n1; ++c) acc += Ar[c] * x[c];
-                y[r] = acc;
-            }
-        CTA_PHASE_END
-    }
-
-    SCP_MFN void add_At(Cta &cta, const double *w, double *vout) const
-    {
-        CTA_PHASE(tid)
-            for (int c = tid; c < n1; c += cta.nt) {
-                double acc = 0.0;
-                for (int r = 0; r < mc; ++r) acc += A[(size_t)r * n1 + c] * w[r];
-                vout[c] += acc;
             }
         CTA_PHASE_END
     }

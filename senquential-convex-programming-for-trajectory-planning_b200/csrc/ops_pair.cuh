@@ -18,129 +18,113 @@ struct PairOp {
     const double *g;      // [nVeh][Hp][2]   (shared)
     const double *H;      // [nVeh][Hp][Hp]  (global, read-only)
     const double *dbar;   // [mc][2]         (shared)
-    double *resp;         // [n][2] scratch  (shared)
+    double *resp;         // [n][2] scratch: response of the last prep'd x   (shared)
+    double *frc;          // [n][2] scratch: forces of the last prep'd w     (shared)
+    double xom, wsum;     // omega component of x / sum of w of the last prep
     double *red;          // reduction scratch
+    double *Msm;          // [n][3] scratch: per (vehicle, step) sum of 4 dd dbar dbar' (xx, xy, yy)
+    double *alpha;        // per-warp scratch for the pair-block products, alpha_slots x alpha_stride doubles
+    int alpha_slots;      // 0: no scratch (large Hp) -> off-diagonal blocks are formed entry by entry
+    int alpha_stride;     // 2 * Hp(Hp+1)/2
 
     SCP_MFN int pair_index(int i, int j) const { return i * nVeh - (i * (i + 1) >> 1) + (j - i - 1); }
 
-    SCP_MFN void mul_P(Cta &cta, const double *x, double *y) const
+    // (P x)[c],  P = blkdiag(2H, 0)
+    SCP_MFN double P_col(int c, const double *x) const
     {
-        CTA_PHASE(tid)
-            for (int c = tid; c <= n; c += cta.nt) {
-                double acc = 0.0;
-                if (c < n) {
-                    const int v = c / Hp;
-                    const double *Hr = H + (size_t)c * Hp;
-                    const double *xv = x + v * Hp;
-                    for (int b = 0; b < Hp; ++b) acc += Hr[b] * xv[b];
-                    acc *= 2.0;
-                }
-                y[c] = acc;
-            }
-        CTA_PHASE_END
+        if (c >= n) return 0.0;
+        const int v = c / Hp;
+        const double *Hr = H + (size_t)c * Hp, *xv = x + v * Hp;
+        double a0 = 0.0, a1 = 0.0;
+        int b = 0;
+        for (; b + 1 < Hp; b += 2) { a0 += Hr[b] * xv[b]; a1 += Hr[b + 1] * xv[b + 1]; }
+        if (b < Hp) a0 += Hr[b] * xv[b];
+        return 2.0 * (a0 + a1);
     }
 
-    SCP_MFN void add_P(Cta &cta, double *S) const
+    // One phase: resp[(v,k)] = sum_{a<=k} g_v[k-a] x[v*Hp+a] (if x) and frc[(v,k)] = F_v(k) = sum over the rows of
+    // vehicle v at step k of sign * 2 * w_r * dbar_r, wsum = sum w (if w).  Afterwards row_dot / col_dot are inline.
+    SCP_MFN void prep(Cta &cta, const double *x, const double *w)
     {
-        CTA_PHASE(tid)
-            const int per = Hp * (Hp + 1) >> 1;
-            for (int e = tid; e < nVeh * per; e += cta.nt) {
-                const int v = e / per;
-                int a, b;
-                scp_tri_decode(e - v * per, &a, &b);
-                S[scp_sidx(v * Hp + a, v * Hp + b)] += 2.0 * H[((size_t)v * Hp + a) * Hp + b];
-            }
-        CTA_PHASE_END
-    }
-
-    // resp[(v,k)] = sum_{a<=k} g_v[k-a] x[v*Hp+a]
-    SCP_MFN void response(Cta &cta, const double *x) const
-    {
-        CTA_PHASE(tid)
-            for (int c = tid; c < n; c += cta.nt) {
-                const int v = c / Hp, k = c - v * Hp;
-                const double *gv = g + (size_t)v * Hp * 2;
-                const double *xv = x + v * Hp;
-                double rx = 0.0, ry = 0.0;
-                for (int a = 0; a <= k; ++a) {
-                    rx += gv[(k - a) * 2] * xv[a];
-                    ry += gv[(k - a) * 2 + 1] * xv[a];
-                }
-                resp[c * 2] = rx;
-                resp[c * 2 + 1] = ry;
-            }
-        CTA_PHASE_END
-    }
-
-    SCP_MFN void mul_A(Cta &cta, const double *x, double *y) const
-    {
-        response(cta, x);
-        CTA_PHASE(tid)
-            const double om = x[n];
-            for (int r = tid; r < mc; r += cta.nt) {
-                double dx, dy;
-                if (r < mcv) {
-                    const int p = r / Hp, k = r - p * Hp;
-                    int i = 0, rem = p;                       // p -> (i, j)
-                    while (rem >= nVeh - 1 - i) { rem -= nVeh - 1 - i; ++i; }
-                    const int j = i + 1 + rem;
-                    dx = resp[(i * Hp + k) * 2] - resp[(j * Hp + k) * 2];
-                    dy = resp[(i * Hp + k) * 2 + 1] - resp[(j * Hp + k) * 2 + 1];
-                } else {
-                    const int q = r - mcv, v = q / (nObst * Hp), k = q % Hp;
-                    dx = resp[(v * Hp + k) * 2];
-                    dy = resp[(v * Hp + k) * 2 + 1];
-                }
-                y[r] = -2.0 * (dbar[r * 2] * dx + dbar[r * 2 + 1] * dy) - om;
-            }
-        CTA_PHASE_END
-    }
-
-    // resp[(v,k)] = F_v(k) = sum over the rows of vehicle v at step k of sign * 2 * w_r * dbar_r ; returns sum w
-    SCP_MFN double forces(Cta &cta, const double *w) const
-    {
+        xom = x ? x[n] : 0.0;
         CTA_RED_BEGIN(cta, 1)
         CTA_PHASE(tid)
             double sw = 0.0;
-            for (int r = tid; r < mc; r += cta.nt) sw += w[r];
+            if (w)
+                for (int r = tid; r < mc; r += cta.nt) sw += w[r];
             for (int c = tid; c < n; c += cta.nt) {
                 const int v = c / Hp, k = c - v * Hp;
-                double fx = 0.0, fy = 0.0;
-                for (int o = 0; o < nVeh; ++o) {
-                    if (o == v) continue;
-                    const int i = v < o ? v : o, j = v < o ? o : v;
-                    const int r = pair_index(i, j) * Hp + k;
-                    const double sw2 = (v == i ? -2.0 : 2.0) * w[r];
-                    fx += sw2 * dbar[r * 2];
-                    fy += sw2 * dbar[r * 2 + 1];
+                if (x) {
+                    const double *gv = g + (size_t)v * Hp * 2;
+                    const double *xv = x + v * Hp;
+                    double rx = 0.0, ry = 0.0;
+                    for (int a = 0; a <= k; ++a) {
+                        rx += gv[(k - a) * 2] * xv[a];
+                        ry += gv[(k - a) * 2 + 1] * xv[a];
+                    }
+                    resp[c * 2] = rx;
+                    resp[c * 2 + 1] = ry;
                 }
-                for (int o = 0; o < nObst; ++o) {
-                    const int r = mcv + (v * nObst + o) * Hp + k;
-                    fx -= 2.0 * w[r] * dbar[r * 2];
-                    fy -= 2.0 * w[r] * dbar[r * 2 + 1];
+                if (w) {
+                    double fx = 0.0, fy = 0.0;
+                    for (int o = 0; o < nVeh; ++o) {
+                        if (o == v) continue;
+                        const int i = v < o ? v : o, j = v < o ? o : v;
+                        const int r = pair_index(i, j) * Hp + k;
+                        const double sw2 = (v == i ? -2.0 : 2.0) * w[r];
+                        fx += sw2 * dbar[r * 2];
+                        fy += sw2 * dbar[r * 2 + 1];
+                    }
+                    for (int o = 0; o < nObst; ++o) {
+                        const int r = mcv + (v * nObst + o) * Hp + k;
+                        fx -= 2.0 * w[r] * dbar[r * 2];
+                        fy -= 2.0 * w[r] * dbar[r * 2 + 1];
+                    }
+                    frc[c * 2] = fx;
+                    frc[c * 2 + 1] = fy;
                 }
-                resp[c * 2] = fx;
-                resp[c * 2 + 1] = fy;
             }
             CTA_RED_SUM(cta, red, 0, tid, sw)
         CTA_PHASE_END_RED(cta, red, 1)
-        return cta_red_sum(cta, red, 0);
+        wsum = cta_red_sum(cta, red, 0);
     }
 
-    SCP_MFN void add_At(Cta &cta, const double *w, double *vout) const
+    // (A x)[r] for the x of the last prep
+    SCP_MFN double row_dot(int r) const
     {
-        const double sw = forces(cta, w);
-        CTA_PHASE(tid)
-            for (int c = tid; c < n; c += cta.nt) {
-                const int v = c / Hp, a = c - v * Hp;
-                const double *gv = g + (size_t)v * Hp * 2;
-                double acc = 0.0;
-                for (int k = a; k < Hp; ++k)
-                    acc += gv[(k - a) * 2] * resp[(v * Hp + k) * 2] + gv[(k - a) * 2 + 1] * resp[(v * Hp + k) * 2 + 1];
-                vout[c] += acc;
-            }
-            if (tid == 0) vout[n] -= sw;
-        CTA_PHASE_END
+        double dx, dy;
+        if (r < mcv) {
+            const int p = r / Hp, k = r - p * Hp;
+            int i = 0, rem = p;
+            while (rem >= nVeh - 1 - i) { rem -= nVeh - 1 - i; ++i; }
+            const int j = i + 1 + rem;
+            dx = resp[(i * Hp + k) * 2] - resp[(j * Hp + k) * 2];
+            dy = resp[(i * Hp + k) * 2 + 1] - resp[(j * Hp + k) * 2 + 1];
+        } else {
+            const int q = r - mcv, v = q / (nObst * Hp), k = q % Hp;
+            dx = resp[(v * Hp + k) * 2];
+            dy = resp[(v * Hp + k) * 2 + 1];
+        }
+        return -2.0 * (dbar[r * 2] * dx + dbar[r * 2 + 1] * dy) - xom;
+    }
+
+    // (A' w)[c] for the w of the last prep
+    SCP_MFN double col_dot(int c) const
+    {
+        if (c >= n) return -wsum;
+        const int v = c / Hp, a = c - v * Hp;
+        const double *gv = g + (size_t)v * Hp * 2;
+        double acc = 0.0;
+        for (int k = a; k < Hp; ++k)
+            acc += gv[(k - a) * 2] * frc[(v * Hp + k) * 2] + gv[(k - a) * 2 + 1] * frc[(v * Hp + k) * 2 + 1];
+        return acc;
+    }
+
+    // resp[(v,k)] = F_v(k) for weights w (used by form_normal for the omega row); returns sum w
+    SCP_MFN double forces(Cta &cta, const double *w)
+    {
+        prep(cta, (const double *)0, w);
+        return wsum;
     }
 
     // coefficient of row r (step k) on u[v, a] without its sign:  2 dbar_r . g_v[k-a]
@@ -149,47 +133,126 @@ struct PairOp {
         return 2.0 * (dbar[r * 2] * gv[l * 2] + dbar[r * 2 + 1] * gv[l * 2 + 1]);
     }
 
-    SCP_MFN void add_AtDA(Cta &cta, const double *dd, double *S) const
+    // S(lower) = blkdiag(2H, 0) + A' diag(dd) A + diag(dg), every entry written exactly once (no clear, no
+    // read-modify-write):
+    //   diagonal blocks   S[(v,a),(v,b)] = 2H_v[a][b] + dg + sum_{k>=a} g_v[k-a]' M_v(k) g_v[k-b],
+    //                     M_v(k) = sum over the rows of v at step k of 4 dd_r dbar_r dbar_r'   (2x2, aggregated)
+    //   omega row         S[n][(v,a)] = -(A'dd)[(v,a)],  S[n][n] = sum dd + dg[n]
+    //   pair blocks (j>i) S[(j,b),(i,a)] = -sum_{k>=max(a,b)} aj[k][b] ai[k][a],  ai = 2 dd_r dbar_r.g_i[k-a],
+    //                     aj = 2 dbar_r.g_j[k-b]: one warp per block, factors staged in its scratch slot.
+    template <class Mem>
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg)
     {
-        const double sd = forces(cta, dd);            // resp = A'dd in force form (for the omega row)
+        double *S = m.S;
+        const double sd = forces(cta, dd);            // frc = A'dd in force form (for the omega row)
         CTA_PHASE(tid)
-            // omega row: S[n][(v,a)] -= (A'dd)[(v,a)] ; S[n][n] += sum dd
+            for (int c = tid; c < n; c += cta.nt) {   // M_v(k)
+                const int v = c / Hp, k = c - v * Hp;
+                double mxx = 0.0, mxy = 0.0, myy = 0.0;
+                for (int o = 0; o < nVeh; ++o) {
+                    if (o == v) continue;
+                    const int r = (v < o ? pair_index(v, o) : pair_index(o, v)) * Hp + k;
+                    const double w4 = 4.0 * dd[r], dx = dbar[r * 2], dy = dbar[r * 2 + 1];
+                    mxx += w4 * dx * dx; mxy += w4 * dx * dy; myy += w4 * dy * dy;
+                }
+                for (int o = 0; o < nObst; ++o) {
+                    const int r = mcv + (v * nObst + o) * Hp + k;
+                    const double w4 = 4.0 * dd[r], dx = dbar[r * 2], dy = dbar[r * 2 + 1];
+                    mxx += w4 * dx * dx; mxy += w4 * dx * dy; myy += w4 * dy * dy;
+                }
+                Msm[c * 3] = mxx; Msm[c * 3 + 1] = mxy; Msm[c * 3 + 2] = myy;
+            }
+            // padding rows/columns of S: zero off-diagonal, unit diagonal (the factorisation keeps them so)
+            for (int c = m.n1 + tid; c < m.n1p; c += cta.nt) {
+                for (int j = 0; j < c; ++j) S[scp_sidx(c, j)] = 0.0;
+                S[scp_sidx(c, c)] = 1.0;
+            }
+        CTA_PHASE_END
+        CTA_PHASE(tid)
+            // omega row
             for (int c = tid; c < n; c += cta.nt) {
                 const int v = c / Hp, a = c - v * Hp;
                 const double *gv = g + (size_t)v * Hp * 2;
                 double acc = 0.0;
                 for (int k = a; k < Hp; ++k)
-                    acc += gv[(k - a) * 2] * resp[(v * Hp + k) * 2] + gv[(k - a) * 2 + 1] * resp[(v * Hp + k) * 2 + 1];
-                S[scp_sidx(n, c)] -= acc;
+                    acc += gv[(k - a) * 2] * frc[(v * Hp + k) * 2] + gv[(k - a) * 2 + 1] * frc[(v * Hp + k) * 2 + 1];
+                S[scp_sidx(n, c)] = -acc;
             }
-            if (tid == 0) S[scp_sidx(n, n)] += sd;
-            // u block, lower triangle
-            const int tot = n * (n + 1) >> 1;
-            for (int e = tid; e < tot; e += cta.nt) {
-                int ci, cj;
-                scp_tri_decode(e, &ci, &cj);
-                const int i = ci / Hp, a = ci - i * Hp, j = cj / Hp, b = cj - j * Hp;
-                const double *gi = g + (size_t)i * Hp * 2, *gj = g + (size_t)j * Hp * 2;
-                double acc = 0.0;
-                if (i == j) {                          // a >= b
-                    for (int o = 0; o < nVeh; ++o) {
-                        if (o == i) continue;
-                        const int r0 = (i < o ? pair_index(i, o) : pair_index(o, i)) * Hp;
-                        for (int k = a; k < Hp; ++k)
-                            acc += dd[r0 + k] * coef2(gi, r0 + k, k - a) * coef2(gi, r0 + k, k - b);
-                    }
-                    for (int o = 0; o < nObst; ++o) {
-                        const int r0 = mcv + (i * nObst + o) * Hp;
-                        for (int k = a; k < Hp; ++k)
-                            acc += dd[r0 + k] * coef2(gi, r0 + k, k - a) * coef2(gi, r0 + k, k - b);
-                    }
-                } else {                               // i > j : rows of pair (j, i); signs -(j) and +(i)
-                    const int r0 = pair_index(j, i) * Hp;
+            if (tid == 0) S[scp_sidx(n, n)] = sd + dg[n];
+            // diagonal blocks
+            const int per = Hp * (Hp + 1) >> 1;
+            for (int e = tid; e < nVeh * per; e += cta.nt) {
+                const int v = e / per;
+                int a, b;
+                scp_tri_decode(e - v * per, &a, &b);
+                const double *gv = g + (size_t)v * Hp * 2;
+                const double *Mv = Msm + (size_t)v * Hp * 3;
+                double acc = 2.0 * H[((size_t)v * Hp + a) * Hp + b] + (a == b ? dg[v * Hp + a] : 0.0);
+                for (int k = a; k < Hp; ++k) {
+                    const double gbx = gv[(k - b) * 2], gby = gv[(k - b) * 2 + 1];
+                    const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;
+                    acc += gv[(k - a) * 2] * bx + gv[(k - a) * 2 + 1] * by;
+                }
+                S[scp_sidx(v * Hp + a, v * Hp + b)] = acc;
+            }
+            // pair blocks without scratch: entry by entry (large horizons)
+            if (alpha_slots == 0) {
+                const int npair = nVeh * (nVeh - 1) >> 1;
+                for (int e = tid; e < npair * Hp * Hp; e += cta.nt) {
+                    const int p = e / (Hp * Hp), rem = e - p * Hp * Hp, b = rem / Hp, a = rem - b * Hp;
+                    int i = 0, q = p;
+                    while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
+                    const int j = i + 1 + q, r0 = p * Hp;
+                    const double *gi = g + (size_t)i * Hp * 2, *gj = g + (size_t)j * Hp * 2;
+                    double acc = 0.0;
                     for (int k = (a > b ? a : b); k < Hp; ++k)
                         acc -= dd[r0 + k] * coef2(gi, r0 + k, k - a) * coef2(gj, r0 + k, k - b);
+                    S[scp_sidx(j * Hp + b, i * Hp + a)] = acc;
                 }
-                S[scp_sidx(ci, cj)] += acc;
             }
         CTA_PHASE_END
+        if (alpha_slots > 0) {
+            const int npair = nVeh * (nVeh - 1) >> 1;
+            const int tri = Hp * (Hp + 1) >> 1, hh = (Hp + 1) >> 1;
+            WARP_SECTION(w, nw)
+                const int nslot = alpha_slots < nw ? alpha_slots : nw;
+                if (w < nslot) {
+                    double *ai = alpha + (size_t)w * alpha_stride, *aj = ai + tri;
+                    for (int p = w; p < npair; p += nslot) {
+                        int i = 0, q = p;
+                        while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
+                        const int j = i + 1 + q, r0 = p * Hp;
+                        const double *gi = g + (size_t)i * Hp * 2, *gj = g + (size_t)j * Hp * 2;
+                        WARP_PHASE(lane)
+                            for (int t = lane; t < tri; t += 32) {
+                                int k, a;
+                                scp_tri_decode(t, &k, &a);
+                                const int r = r0 + k;
+                                ai[t] = dd[r] * coef2(gi, r, k - a);
+                                aj[t] = coef2(gj, r, k - a);
+                            }
+                        WARP_PHASE_END
+                        WARP_PHASE(lane)
+                            for (int t = lane; t < hh * hh; t += 32) {          // 2x2 patches of the Hp x Hp block
+                                const int b0 = (t / hh) * 2, a0 = (t - (t / hh) * hh) * 2;
+                                const bool b1ok = b0 + 1 < Hp, a1ok = a0 + 1 < Hp;
+                                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                                for (int k = (a0 > b0 ? a0 : b0); k < Hp; ++k) {
+                                    const int kb = k * (k + 1) >> 1;
+                                    const double x0 = ai[kb + a0], x1 = (a1ok && a0 + 1 <= k) ? ai[kb + a0 + 1] : 0.0;
+                                    const double y0 = aj[kb + b0], y1 = (b1ok && b0 + 1 <= k) ? aj[kb + b0 + 1] : 0.0;
+                                    c00 += y0 * x0; c01 += y0 * x1; c10 += y1 * x0; c11 += y1 * x1;
+                                }
+                                S[scp_sidx(j * Hp + b0, i * Hp + a0)] = -c00;
+                                if (a1ok) S[scp_sidx(j * Hp + b0, i * Hp + a0 + 1)] = -c01;
+                                if (b1ok) S[scp_sidx(j * Hp + b0 + 1, i * Hp + a0)] = -c10;
+                                if (a1ok && b1ok) S[scp_sidx(j * Hp + b0 + 1, i * Hp + a0 + 1)] = -c11;
+                            }
+                        WARP_PHASE_END
+                    }
+                }
+            WARP_SECTION_END
+            CTA_SYNC
+        }
     }
 };

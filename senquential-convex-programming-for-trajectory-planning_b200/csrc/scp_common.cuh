@@ -28,7 +28,10 @@
 #define SCP_DEVICE_BUILD 0
 #endif
 
-#define SCP_MAX_WARPS 32
+#ifndef SCP_MAX_THREADS
+#define SCP_MAX_THREADS 256      // upper bound on threads per CTA of every kernel in this library
+#endif
+#define SCP_MAX_WARPS (SCP_MAX_THREADS / 32)
 #define SCP_TILE 8
 #define SCP_TILE2 64
 
@@ -69,6 +72,26 @@ static inline int scp_emu_tid(const Cta &c, int i) { return c.reverse ? c.nt - 1
             }                                                                          \
             (red)[s_ * SCP_MAX_WARPS + w_] = v_[0];                                    \
         }
+#endif
+
+// Warp sections: inside WARP_SECTION each warp works on its own data; WARP_PHASE ... WARP_PHASE_END separates
+// steps that exchange data between the lanes of one warp through shared memory (__syncwarp).  A CTA_SYNC must
+// follow a warp section before other warps consume its results.
+#if SCP_DEVICE_BUILD
+#define WARP_SECTION(w, nw) { const int w = (int)threadIdx.x >> 5; const int nw = cta.nt >> 5;
+#define WARP_SECTION_END }
+#define WARP_PHASE(lane) { const int lane = (int)threadIdx.x & 31;
+#define WARP_PHASE_END } __syncwarp();
+#define CTA_SYNC __syncthreads();
+#else
+#define WARP_SECTION(w, nw)                                                                       \
+    for (int w##_i = 0; w##_i < (cta.nt >> 5); ++w##_i) {                                         \
+        const int w = cta.reverse ? (cta.nt >> 5) - 1 - w##_i : w##_i;                            \
+        const int nw = cta.nt >> 5;
+#define WARP_SECTION_END }
+#define WARP_PHASE(lane) for (int lane##_i = 0; lane##_i < 32; ++lane##_i) { const int lane = cta.reverse ? 31 - lane##_i : lane##_i;
+#define WARP_PHASE_END }
+#define CTA_SYNC
 #endif
 
 // Inside a reducing phase every thread calls these exactly once per slot (uniform control flow).
@@ -116,6 +139,27 @@ SCP_FN double cta_red_max(const Cta &cta, const double *red, int slot)
     return t;
 }
 
+// ------------------------------------------------------------------------------------------------ phase timers
+// Tuning builds (-DSCP_PHASE_TIMERS) accumulate, per code region, the cycles thread 0 of every CTA spends between
+// consecutive marks (regions end at CTA barriers, so thread 0's clock is the CTA's).  Off in the product build.
+#if SCP_DEVICE_BUILD && defined(SCP_PHASE_TIMERS)
+__device__ unsigned long long g_scp_prof[32];
+#define SCP_TIMER_DECL long long scp_t_last = clock64();
+#define SCP_TIMER(id)                                                                         \
+    if (threadIdx.x == 0) {                                                                   \
+        const long long t_ = clock64();                                                       \
+        atomicAdd(&g_scp_prof[id], (unsigned long long)(t_ - scp_t_last));                    \
+        scp_t_last = t_;                                                                      \
+    }
+#define SCP_TIMER_ARG , long long &scp_t_last
+#define SCP_TIMER_PASS , scp_t_last
+#else
+#define SCP_TIMER_DECL
+#define SCP_TIMER(id)
+#define SCP_TIMER_ARG
+#define SCP_TIMER_PASS
+#endif
+
 // ------------------------------------------------------------------------------------------------ misc
 SCP_HDFN int scp_imin(int a, int b) { return a < b ? a : b; }
 SCP_HDFN int scp_imax(int a, int b) { return a > b ? a : b; }
@@ -123,15 +167,20 @@ SCP_HDFN int scp_round_up(int a, int m) { return (a + m - 1) / m * m; }
 
 // index of lower-triangular tile (I, J), J <= I, in the tile-packed normal matrix
 SCP_HDFN int scp_tile_off(int I, int J) { return ((I * (I + 1) >> 1) + J) * SCP_TILE2; }
+// Position of element (r, c) inside an 8x8 tile.  Rows are 64 bytes; in rows 2,3,6,7 the two 32-byte halves
+// are swapped.  With plain row-major tiles rows r and r+2 share shared-memory banks, so the column-shaped
+// accesses of the FP64 mma fragments (8 rows x 32 bytes) would be 4-way bank-conflicted; with the swap rows
+// 0..3 cover all 32 banks and a fragment load costs the minimum of two wavefronts.
+SCP_HDFN constexpr int scp_tphys(int r, int c) { return (r << 3) + ((((c >> 2) ^ (r >> 1)) & 1) << 2) + (c & 3); }
 // element (ci, cj), ci >= cj
 SCP_HDFN int scp_sidx(int ci, int cj)
 {
-    return scp_tile_off(ci >> 3, cj >> 3) + ((ci & 7) << 3) + (cj & 7);
+    return scp_tile_off(ci >> 3, cj >> 3) + scp_tphys(ci & 7, cj & 7);
 }
 // t -> (ii, jj) with ii >= jj, t = ii(ii+1)/2 + jj
 SCP_HDFN void scp_tri_decode(int t, int *ii, int *jj)
 {
-    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);      // estimate, corrected below
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
     *ii = i;

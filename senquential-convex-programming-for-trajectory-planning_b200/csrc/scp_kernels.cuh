@@ -523,70 +523,109 @@ SCP_FN void scp_linearise(Cta &cta, int nVeh, int Hp, int nObst, const double *g
 }
 
 // ================================================================================================ working set
+// Two-pool bump allocator for a CTA's working set: shared memory first; whatever does not fit under `sh_lim`
+// overflows into the CTA's slice of the global workspace (L2-resident).  The same function runs on the host
+// (null bases) to size both pools, so the layout is a pure function of the problem dimensions.
 struct ScpBump {
-    double *base;
-    size_t off;
+    double *sh;
+    size_t sh_off, sh_lim;      // doubles
+    double *gl;
+    size_t gl_off;
+    bool all_shared;            // compile-time true in the kernels instantiated for fully shared-resident sets
+    bool last_shared;
     SCP_HDMFN double *take(size_t nd)
     {
-        double *p = base ? base + off : 0;
-        off += (nd + 1) & ~(size_t)1;      // keep 16-byte alignment
+        nd = (nd + 1) & ~(size_t)1;      // keep 16-byte alignment
+        if (all_shared || sh_off + nd <= sh_lim) {
+            double *p = sh ? sh + sh_off : 0;
+            sh_off += nd;
+            last_shared = true;
+            return p;
+        }
+        double *p = gl ? gl + gl_off : 0;
+        gl_off += nd;
+        last_shared = false;
         return p;
     }
 };
 
-// Carve the interior-point working set out of `sh` (shared memory); S comes from `Sglobal` when it does not fit.
-SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, double *Sglobal, bool S_in_shared)
+SCP_HDFN ScpBump scp_bump(double *sh, size_t sh_lim, double *gl, bool all_shared)
+{
+    ScpBump bp;
+    bp.sh = sh; bp.sh_off = 0; bp.sh_lim = sh_lim; bp.gl = gl; bp.gl_off = 0; bp.all_shared = all_shared; bp.last_shared = true;
+    return bp;
+}
+
+// Vectors of the interior-point working set (small and hot first); the tile scratch and the normal matrix are
+// carved last by ipm_carve_big so that they are the first to overflow.
+SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc)
 {
     m.n1 = n1; m.n1p = scp_round_up(n1, SCP_TILE); m.T = m.n1p / SCP_TILE; m.mc = mc;
-    const size_t Sd = (size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2;
-    m.S = S_in_shared ? bp.take(Sd) : Sglobal;
-    m.Linv = bp.take((size_t)m.T * SCP_TILE2);
-    m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
-    m.bA = bp.take(mc); m.sA = bp.take(mc); m.zA = bp.take(mc); m.rzA = bp.take(mc);
-    m.dsA = bp.take(mc); m.dzA = bp.take(mc); m.ccA = bp.take(mc);
-    m.ub = bp.take(m.n1p); m.sU = bp.take(m.n1p); m.zU = bp.take(m.n1p); m.dsU = bp.take(m.n1p);
-    m.dzU = bp.take(m.n1p); m.ccU = bp.take(m.n1p);
-    m.lb = bp.take(m.n1p); m.sL = bp.take(m.n1p); m.zL = bp.take(m.n1p); m.dsL = bp.take(m.n1p);
-    m.dzL = bp.take(m.n1p); m.ccL = bp.take(m.n1p);
     m.red = bp.take(8 * SCP_MAX_WARPS);
     m.t8 = bp.take(16);
+    m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
+    m.dinv = bp.take(m.n1p);
+    m.ub = bp.take(m.n1p); m.sU = bp.take(m.n1p); m.zU = bp.take(m.n1p); m.dsU = bp.take(m.n1p);
+    m.dzU = bp.take(m.n1p); m.ccU = bp.take(m.n1p); m.eU = bp.take(m.n1p);
+    m.lb = bp.take(m.n1p); m.sL = bp.take(m.n1p); m.zL = bp.take(m.n1p); m.dsL = bp.take(m.n1p);
+    m.dzL = bp.take(m.n1p); m.ccL = bp.take(m.n1p); m.eL = bp.take(m.n1p);
+    m.bA = bp.take(mc); m.sA = bp.take(mc); m.zA = bp.take(mc); m.rzA = bp.take(mc);
+    m.dsA = bp.take(mc); m.dzA = bp.take(mc); m.ccA = bp.take(mc); m.eA = bp.take(mc);
 }
 
-SCP_HDFN size_t ipm_S_doubles(int n1)
+SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 {
-    const int T = scp_round_up(n1, SCP_TILE) / SCP_TILE;
-    return (size_t)(T * (T + 1) / 2) * SCP_TILE2;
-}
-
-SCP_HDFN size_t ipm_shared_doubles(int n1, int mc, bool S_in_shared)
-{
-    ScpBump bp = {0, 0};
-    IpmMem m;
-    ipm_carve(bp, m, n1, mc, 0, S_in_shared);
-    return bp.off;
+    m.wbuf = bp.take((size_t)(m.T * 64 > 4 * m.n1p ? m.T * 64 : 4 * m.n1p));
+    m.S = bp.take((size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2);
 }
 
 struct ScpMem {
     IpmMem ipm;
-    double *g, *dbar, *resp, *ucur;
+    double *g, *dbar, *resp, *frc, *ucur, *Msm, *alpha, *Hs;
+    int alpha_slots, alpha_stride;
+    bool H_local;      // Hs is shared-resident: the instance's cost blocks are copied there once per instance
 };
 
-SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, double *Sglobal, bool S_in_shared)
+// alpha_slots: number of per-warp scratch slots for the pair-block products of the normal matrix (0 = none)
+// want_H: keep a shared-memory copy of the instance's cost blocks (read every iteration); otherwise they are read
+// from global memory.
+SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int alpha_slots, int want_H)
 {
     const int n = nVeh * Hp, mc = Hp * (nVeh * (nVeh - 1) / 2 + nVeh * nObst);
-    ipm_carve(bp, s.ipm, n + 1, mc, Sglobal, S_in_shared);
+    ipm_carve(bp, s.ipm, n + 1, mc);
     s.g = bp.take((size_t)n * 2);
     s.dbar = bp.take((size_t)mc * 2);
     s.resp = bp.take((size_t)n * 2);
+    s.frc = bp.take((size_t)n * 2);
     s.ucur = bp.take(s.ipm.n1p);
+    s.Msm = bp.take((size_t)n * 3);
+    s.alpha_slots = alpha_slots;
+    s.alpha_stride = Hp * (Hp + 1);
+    s.alpha = bp.take((size_t)alpha_slots * s.alpha_stride);
+    s.Hs = want_H ? bp.take((size_t)n * Hp) : 0;
+    s.H_local = want_H && bp.last_shared;
+    ipm_carve_big(bp, s.ipm);
 }
 
-SCP_HDFN size_t scp_shared_doubles(int nVeh, int Hp, int nObst, bool S_in_shared)
+// total doubles of the working set / split under a shared-memory limit (host-side planning)
+SCP_HDFN void scp_footprint(int nVeh, int Hp, int nObst, int alpha_slots, int want_H, size_t sh_lim, size_t *sh_used,
+                            size_t *gl_used)
 {
-    ScpBump bp = {0, 0};
+    ScpBump bp = scp_bump(0, sh_lim, 0, false);
     ScpMem s;
-    scp_carve(bp, s, nVeh, Hp, nObst, 0, S_in_shared);
-    return bp.off;
+    scp_carve(bp, s, nVeh, Hp, nObst, alpha_slots, want_H);
+    *sh_used = bp.sh_off;
+    *gl_used = bp.gl_off;
+}
+
+SCP_HDFN void ipm_footprint(int n1, int mc, size_t sh_lim, size_t *sh_used, size_t *gl_used)
+{
+    ScpBump bp = scp_bump(0, sh_lim, 0, false);
+    IpmMem m;
+    ipm_carve(bp, m, n1, mc);
+    ipm_carve_big(bp, m);
+    *sh_used = bp.sh_off;
+    *gl_used = bp.gl_off;
 }
 
 // ================================================================================================ K4: the SCP loop
@@ -617,11 +656,15 @@ SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
 
     PairOp op;
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
-    op.g = s.g; op.H = HB; op.dbar = s.dbar; op.resp = s.resp; op.red = m.red;
+    op.g = s.g; op.H = s.H_local ? s.Hs : HB; op.dbar = s.dbar; op.resp = s.resp; op.frc = s.frc; op.red = m.red;
+    op.xom = 0.0; op.wsum = 0.0;
+    op.Msm = s.Msm; op.alpha = s.alpha; op.alpha_slots = s.alpha_slots; op.alpha_stride = s.alpha_stride;
 
     // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
     CTA_PHASE(tid)
         for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = gB[e];
+        if (s.H_local)
+            for (int e = tid; e < n * Hp; e += cta.nt) s.Hs[e] = HB[e];
         for (int c = tid; c < m.n1p; c += cta.nt) {
             double uv = 0.0;
             if (c < n) {
@@ -722,6 +765,7 @@ SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc,
     op.n1 = n1; op.mc = mc;
     op.P = io.P + (size_t)b * n1 * n1;
     op.A = io.A + (size_t)b * mc * n1;
+    op.xp = 0; op.wp = 0;
     CTA_PHASE(tid)
         for (int c = tid; c < m.n1p; c += cta.nt) {
             m.q[c] = c < n1 ? io.q[(size_t)b * n1 + c] : 0.0;
@@ -754,7 +798,7 @@ SCP_FN void scp_assemble_instance(Cta &cta, const scpb200_dims &d, const scpb200
 {
     const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp, n1 = n + 1;
     const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
-    ScpBump bp = {sh, 0};
+    ScpBump bp = scp_bump(sh, (size_t)1 << 40, (double *)0, true);
     double *pos = bp.take((size_t)n * 2), *dbar = bp.take((size_t)mc * 2), *bA = bp.take(mc);
     double *gs = bp.take((size_t)n * 2), *us = bp.take(n);
     const double *gB = g + (size_t)b * n * 2, *cB = cterm + (size_t)b * n * 2;

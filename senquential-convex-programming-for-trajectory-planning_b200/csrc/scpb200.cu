@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(128) k_advance_linear(scpb200_dims d, const do
     }
 }
 
+#ifndef SCP_MIN_CTAS
+#define SCP_MIN_CTAS 2
+#endif
+
 // Persistent CTAs pull instance indices from a global counter (SCP/IPM iteration counts vary per instance).
 __device__ __forceinline__ int next_instance(int *counter, int *slot)
 {
@@ -187,66 +191,81 @@ __device__ __forceinline__ int next_instance(int *counter, int *slot)
     return *slot;
 }
 
-template <bool S_SHARED>
-__global__ void k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, int *counter, double *Sws, size_t S_stride)
+template <bool ALL_SHARED>
+__global__ void __launch_bounds__(SCP_MAX_THREADS, SCP_MIN_CTAS)
+k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, int *counter, double *gws, size_t gl_stride, size_t sh_lim,
+            int alpha_slots, int want_H)
 {
     extern __shared__ double sh[];
     __shared__ int slot;
     Cta cta = {(int)blockDim.x};
-    ScpBump bp = {sh, 0};
+    ScpBump bp = scp_bump(sh, sh_lim, ALL_SHARED ? (double *)0 : gws + (size_t)blockIdx.x * gl_stride, ALL_SHARED);
     ScpMem s;
-    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, S_SHARED ? (double *)0 : Sws + (size_t)blockIdx.x * S_stride, S_SHARED);
+    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H);
     for (int b = next_instance(counter, &slot); b < d.B; b = next_instance(counter, &slot))
         scp_solve_instance(cta, d, p, b, io, s);
 }
 
-template <bool S_SHARED>
-__global__ void k_qp_dense(int B, scpb200_params p, int n1, int mc, QpIO io, int *counter, double *Sws, size_t S_stride)
+template <bool ALL_SHARED>
+__global__ void __launch_bounds__(SCP_MAX_THREADS, 1)
+k_qp_dense(int B, scpb200_params p, int n1, int mc, QpIO io, int *counter, double *gws, size_t gl_stride, size_t sh_lim)
 {
     extern __shared__ double sh[];
     __shared__ int slot;
     Cta cta = {(int)blockDim.x};
-    ScpBump bp = {sh, 0};
+    ScpBump bp = scp_bump(sh, sh_lim, ALL_SHARED ? (double *)0 : gws + (size_t)blockIdx.x * gl_stride, ALL_SHARED);
     IpmMem m;
-    ipm_carve(bp, m, n1, mc, S_SHARED ? (double *)0 : Sws + (size_t)blockIdx.x * S_stride, S_SHARED);
+    ipm_carve(bp, m, n1, mc);
+    ipm_carve_big(bp, m);
     for (int b = next_instance(counter, &slot); b < B; b = next_instance(counter, &slot))
         qp_solve_instance(cta, p, n1, mc, b, io, m);
 }
 
 // ------------------------------------------------------------------------------------------------ launch planning
 struct SolvePlan {
-    int threads, grid, S_shared;
-    size_t smem_bytes, S_stride;    // S_stride in doubles (0 when S is in shared memory)
+    int threads, grid, all_shared, alpha_slots, ctas_per_sm, want_H;
+    size_t smem_bytes, sh_lim, gl_stride;    // sh_lim / gl_stride in doubles
     size_t ws_bytes;
 };
 
 #define WS_HEADER 256
+#define SCP_SM_SHARED_BYTES 233472      /* 228 KiB per SM on B200, 1 KiB reserved per resident CTA */
 
-template <class KS, class KG>
-static int plan_common(KS kshared, KG kglobal, size_t sh_with_S, size_t sh_without_S, size_t S_doubles, int B,
-                       SolvePlan *pl)
+// Pick the occupancy target: the largest number of CTAs per SM (<= max_ctas) for which the whole working set is
+// shared-resident; if it does not fit even alone, one CTA per SM with the tail of the set in the global workspace.
+template <class KS, class KG, class FP>
+static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B, SolvePlan *pl)
 {
     DevInfo di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    pl->threads = env_int("SCPB200_THREADS", 256);
-    if (pl->threads % 32 || pl->threads < 32 || pl->threads > 1024) return set_err(SCPB200_ERR_ARG, "SCPB200_THREADS must be a multiple of 32 in [32,1024]");
-    const size_t lim = (size_t)di.smem_optin;
+    if (pl->threads % 32 || pl->threads < 32 || pl->threads > SCP_MAX_THREADS)
+        return set_err(SCPB200_ERR_ARG, "SCPB200_THREADS must be a multiple of 32 in [32, SCP_MAX_THREADS]");
+    size_t shu = 0, glu = 0;
+    const bool force_global = env_int("SCPB200_FORCE_GLOBAL_S", 0) != 0;
     int occ = 0;
-    if (sh_with_S * 8 <= lim && !env_int("SCPB200_FORCE_GLOBAL_S", 0)) {
-        pl->S_shared = 1;
-        pl->smem_bytes = sh_with_S * 8;
-        pl->S_stride = 0;
+    pl->all_shared = 0;
+    for (int k = max_ctas; k >= 1 && !force_global; --k) {
+        const size_t lim = ((size_t)SCP_SM_SHARED_BYTES / k - 1024) / 8;
+        footprint((size_t)1 << 40, &shu, &glu);
+        if (shu <= lim && shu * 8 <= (size_t)di.smem_optin) { pl->all_shared = 1; pl->ctas_per_sm = k; break; }
+    }
+    if (pl->all_shared) {
+        pl->sh_lim = (size_t)1 << 40;
+        pl->smem_bytes = shu * 8;
+        pl->gl_stride = 0;
         CUDA_TRY(cudaFuncSetAttribute(kshared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kshared, pl->threads, pl->smem_bytes));
-    } else if (sh_without_S * 8 <= lim) {
-        pl->S_shared = 0;
-        pl->smem_bytes = sh_without_S * 8;
-        pl->S_stride = S_doubles;
+    } else {
+        size_t lim = (size_t)di.smem_optin / 8;
+        if (force_global) lim = lim / 3;                       // testing aid: push the big arrays out
+        footprint(lim, &shu, &glu);
+        pl->sh_lim = lim;
+        pl->smem_bytes = shu * 8;
+        pl->gl_stride = glu;
+        pl->ctas_per_sm = 1;
         CUDA_TRY(cudaFuncSetAttribute(kglobal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kglobal, pl->threads, pl->smem_bytes));
-    } else {
-        return set_err(SCPB200_ERR_SIZE, "problem too large: the per-instance vectors exceed shared memory");
     }
     if (occ < 1) return set_err(SCPB200_ERR_SIZE, "kernel cannot be resident (occupancy 0)");
     const int cap = env_int("SCPB200_CTAS_PER_SM", 0);
@@ -255,21 +274,45 @@ static int plan_common(KS kshared, KG kglobal, size_t sh_with_S, size_t sh_witho
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     pl->grid = (int)grid;
-    pl->ws_bytes = WS_HEADER + (pl->S_shared ? 0 : (size_t)di.sms * occ * S_doubles * 8);
+    pl->ws_bytes = WS_HEADER + (size_t)di.sms * occ * pl->gl_stride * 8;
     return 0;
 }
 
 static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
 {
-    const int n1 = d->nVeh * d->Hp + 1;
-    return plan_common(k_scp_solve<true>, k_scp_solve<false>, scp_shared_doubles(d->nVeh, d->Hp, d->nObst, true),
-                       scp_shared_doubles(d->nVeh, d->Hp, d->nObst, false), ipm_S_doubles(n1), d->B, pl);
+    pl->threads = env_int("SCPB200_THREADS", 256);
+    const int nVeh = d->nVeh, Hp = d->Hp, nObst = d->nObst;
+    // per-warp scratch slots for the pair-block products: one per warp if that keeps the occupancy target,
+    // else fewer
+    int slots = pl->threads / 32;
+    const int want = env_int("SCPB200_ALPHA_SLOTS", -1);
+    if (want >= 0 && want < slots) slots = want;
+    const size_t target = ((size_t)SCP_SM_SHARED_BYTES / SCP_MIN_CTAS - 1024) / 8;
+    while (slots > 1) {
+        size_t shu, glu;
+        scp_footprint(nVeh, Hp, nObst, slots, 1, (size_t)1 << 40, &shu, &glu);
+        if (shu <= target) break;
+        slots /= 2;
+    }
+    if (Hp > 24) slots = 0;                                    // long horizons: entry-by-entry pair blocks
+    pl->alpha_slots = slots;
+    // first with the cost blocks shared-resident, then without
+    for (int want_H = 1; want_H >= 0; --want_H) {
+        auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu); };
+        int rc = plan_common(k_scp_solve<true>, k_scp_solve<false>, fp, SCP_MIN_CTAS, d->B, pl);
+        pl->want_H = want_H;
+        if (rc || pl->all_shared || want_H == 0) return rc;
+    }
+    return 0;
 }
 
 static int plan_qp(int n1, int mc, int B, SolvePlan *pl)
 {
-    return plan_common(k_qp_dense<true>, k_qp_dense<false>, ipm_shared_doubles(n1, mc, true),
-                       ipm_shared_doubles(n1, mc, false), ipm_S_doubles(n1), B, pl);
+    pl->threads = env_int("SCPB200_THREADS", 256);
+    pl->alpha_slots = 0;
+    pl->want_H = 0;
+    auto fp = [=](size_t lim, size_t *shu, size_t *glu) { ipm_footprint(n1, mc, lim, shu, glu); };
+    return plan_common(k_qp_dense<true>, k_qp_dense<false>, fp, 1, B, pl);
 }
 
 extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
@@ -435,11 +478,11 @@ extern "C" int scpb200_qp_solve_dense(const scpb200_dims *d, const scpb200_param
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
     int *counter = (int *)ws;
-    double *Sws = (double *)((char *)ws + WS_HEADER);
-    if (pl.S_shared)
-        k_qp_dense<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, Sws, pl.S_stride);
+    double *gws = (double *)((char *)ws + WS_HEADER);
+    if (pl.all_shared)
+        k_qp_dense<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, gws, pl.gl_stride, pl.sh_lim);
     else
-        k_qp_dense<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, Sws, pl.S_stride);
+        k_qp_dense<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(d->B, *p, n1, mc, io, counter, gws, pl.gl_stride, pl.sh_lim);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -465,17 +508,32 @@ extern "C" int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p,
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
     int *counter = (int *)ws;
-    double *Sws = (double *)((char *)ws + WS_HEADER);
-    if (pl.S_shared)
-        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, Sws, pl.S_stride);
+    double *gws = (double *)((char *)ws + WS_HEADER);
+    if (pl.all_shared)
+        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, gws, pl.gl_stride, pl.sh_lim,
+                                                                     pl.alpha_slots, pl.want_H);
     else
-        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, Sws, pl.S_stride);
+        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, gws, pl.gl_stride, pl.sh_lim,
+                                                                      pl.alpha_slots, pl.want_H);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
+#ifdef SCP_PHASE_TIMERS
+// tuning builds only: read (and clear) the per-region cycle counters
+extern "C" int scpb200_debug_read_timers(unsigned long long *out32)
+{
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out32, g_scp_prof, sizeof(unsigned long long) * 32));
+    unsigned long long z[32] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_scp_prof, z, sizeof z));
+    return 0;
+}
+#endif
+
 // launch geometry the solver would use for these dims (diagnostics for bench.py / DESIGN.md):
-// out[0]=grid, out[1]=threads, out[2]=dynamic shared bytes, out[3]=S in shared (1/0), out[4]=SM count
+// out[0]=grid, out[1]=threads, out[2]=dynamic shared bytes, out[3]=S in shared (1/0), out[4]=SM count,
+// out[5]=pair-block scratch slots
 extern "C" int scpb200_scp_plan(const scpb200_dims *d, int64_t *out)
 {
     int rc = check_dims(d);
@@ -486,6 +544,7 @@ extern "C" int scpb200_scp_plan(const scpb200_dims *d, int64_t *out)
     DevInfo di;
     rc = dev_info(&di);
     if (rc) return rc;
-    out[0] = pl.grid; out[1] = pl.threads; out[2] = (int64_t)pl.smem_bytes; out[3] = pl.S_shared; out[4] = di.sms;
+    out[0] = pl.grid; out[1] = pl.threads; out[2] = (int64_t)pl.smem_bytes; out[3] = pl.all_shared; out[4] = di.sms;
+    out[5] = pl.alpha_slots;
     return 0;
 }

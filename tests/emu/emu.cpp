@@ -13,13 +13,14 @@
 
 #include "../../senquential-convex-programming-for-trajectory-planning_b200/csrc/scp_kernels.cuh"
 
-static int g_nt = 128, g_reverse = 0, g_force_global_S = 0;
+static int g_nt = 128, g_reverse = 0, g_force_global_S = 0, g_alpha_slots = -1;
 
-extern "C" void emu_config(int nt, int reverse, int force_global_S)
+extern "C" void emu_config(int nt, int reverse, int force_global_S, int alpha_slots)
 {
     g_nt = nt;
     g_reverse = reverse;
     g_force_global_S = force_global_S;
+    g_alpha_slots = alpha_slots;          // -1: one scratch slot per warp
 }
 
 static Cta *new_cta()
@@ -89,11 +90,14 @@ extern "C" int emu_qp_solve_dense(const scpb200_dims *d, const scpb200_params *p
                                   const double *ub, double *x, double *fval, int32_t *iters, int32_t *status, double *zA)
 {
     Cta *cta = new_cta();
-    const bool sh = !g_force_global_S;
-    std::vector<double> smem(ipm_shared_doubles(n1, mc, sh)), Sg(ipm_S_doubles(n1));
-    ScpBump bp = {smem.data(), 0};
+    size_t shu, glu;
+    const size_t lim = g_force_global_S ? 2000 : ((size_t)1 << 40);
+    ipm_footprint(n1, mc, lim, &shu, &glu);
+    std::vector<double> smem(shu + 2), gmem(glu + 2);
+    ScpBump bp = scp_bump(smem.data(), lim, gmem.data(), false);
     IpmMem m;
-    ipm_carve(bp, m, n1, mc, Sg.data(), sh);
+    ipm_carve(bp, m, n1, mc);
+    ipm_carve_big(bp, m);
     QpIO io = {P, q, A, b, lb, ub, x, fval, zA, iters, status};
     for (int bi = 0; bi < d->B; ++bi) qp_solve_instance(*cta, *p, n1, mc, bi, io, m);
     free(cta);
@@ -107,11 +111,14 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
                              double *max_violation)
 {
     Cta *cta = new_cta();
-    const bool sh = !g_force_global_S;
-    std::vector<double> smem(scp_shared_doubles(d->nVeh, d->Hp, d->nObst, sh)), Sg(ipm_S_doubles(d->nVeh * d->Hp + 1));
-    ScpBump bp = {smem.data(), 0};
+    const int slots = g_alpha_slots < 0 ? g_nt / 32 : g_alpha_slots;
+    size_t shu, glu;
+    const size_t lim = g_force_global_S ? 3000 : ((size_t)1 << 40);
+    scp_footprint(d->nVeh, d->Hp, d->nObst, slots, 1, lim, &shu, &glu);
+    std::vector<double> smem(shu + 2), gmem(glu + 2);
+    ScpBump bp = scp_bump(smem.data(), lim, gmem.data(), false);
     ScpMem s;
-    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, Sg.data(), sh);
+    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1);
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
     for (int b = 0; b < d->B; ++b) scp_solve_instance(*cta, *d, *p, b, io, s);
@@ -131,5 +138,7 @@ extern "C" int emu_ode_predict(const scpb200_dims *d, const scpb200_params *p, c
 
 extern "C" size_t emu_scp_shared_bytes(int nVeh, int Hp, int nObst, int S_in_shared)
 {
-    return scp_shared_doubles(nVeh, Hp, nObst, S_in_shared != 0) * 8;
+    size_t shu, glu;
+    scp_footprint(nVeh, Hp, nObst, g_alpha_slots < 0 ? g_nt / 32 : g_alpha_slots, 1, S_in_shared ? ((size_t)1 << 40) : 3000, &shu, &glu);
+    return shu * 8;
 }

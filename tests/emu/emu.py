@@ -40,8 +40,8 @@ def lib():
     return _lib
 
 
-def config(nt=128, reverse=False, force_global_S=False):
-    lib().emu_config(C.c_int(nt), C.c_int(int(reverse)), C.c_int(int(force_global_S)))
+def config(nt=128, reverse=False, force_global_S=False, alpha_slots=-1):
+    lib().emu_config(C.c_int(nt), C.c_int(int(reverse)), C.c_int(int(force_global_S)), C.c_int(alpha_slots))
 
 
 def _d(a):

@@ -174,6 +174,27 @@ def test_scp_kernel_teacher_forced(oracle, fname, reverse):
         assert (r["status"][it] & (capi.ST_QP_MAXITER | capi.ST_QP_PIVOT)) == 0
 
 
+@pytest.mark.parametrize("slots", [0, 1, 3])
+def test_scp_kernel_pair_block_scratch_variants(oracle, slots):
+    """The normal-matrix pair blocks are formed per warp through a scratch slot; fewer slots than warps and the
+    scratch-free entry-by-entry path (large horizons) must give the same iterates."""
+    G = load_golden("circle8_hp10_step10.npz")
+    S = _setup(oracle, G)
+    nit = int(G["scp_iters"])
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    p = params_for(G, max_scp_iter=1)
+    args = (rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
+            G["prev_u"][:nit], p)
+    emu.config(nt=128, alpha_slots=-1)
+    base = emu.scp_solve(*args)
+    emu.config(nt=128, alpha_slots=slots)
+    r = emu.scp_solve(*args)
+    assert np.abs(r["u"] - base["u"]).max() < 1e-9
+    assert (r["ipm_iters"] == base["ipm_iters"]).all()
+    for it in range(nit):
+        assert np.abs(r["u"][it] - G["x"][it][:-1]).max() < 1e-6
+
+
 @pytest.mark.parametrize("fname", FAST_FILES)
 def test_scp_kernel_free_running(oracle, fname):
     """K4 free-running from the reference's warm start: iteration count and converged u (where the SCP map is
