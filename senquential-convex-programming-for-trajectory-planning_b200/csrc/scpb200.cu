@@ -84,6 +84,10 @@ static int check_dims(const scpb200_dims *d)
     return 0;
 }
 
+#ifndef SCP_ASM_MIN_CTAS
+#define SCP_ASM_MIN_CTAS 6
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_mpc_setup(scpb200_dims d, scpb200_params p, const double *x0, const double *u0,
                                                    const double *veh, const double *poly, double *ref, double *g,
@@ -100,12 +104,18 @@ __global__ void __launch_bounds__(128) k_mpc_setup(scpb200_dims d, scpb200_param
 __global__ void __launch_bounds__(256) k_assemble(scpb200_dims d, scpb200_params p, const double *g, const double *cterm,
                                                   const double *H, const double *qv, const double *ubar,
                                                   const double *dsafe, const double *dsafe_obst, const double *obst,
-                                                  double *P, double *q, double *A, double *bvec, double *lb, double *ub)
+                                                  double *P, double *q, double *A, double *bvec, double *lb, double *ub,
+                                                  int nparts)
 {
     extern __shared__ double sh[];
     Cta cta = {(int)blockDim.x};
-    for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
-        scp_assemble_instance(cta, d, p, b, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, bvec, lb, ub, sh);
+    for (int e = threadIdx.x; e < SCP_ASM_ZBUF; e += blockDim.x) sh[e] = 0.0;      // the zero source of the bulk stores
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                     // -> visible to the async proxy
+    __syncthreads();
+    const long nitems = (long)d.B * nparts;
+    for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+        scp_assemble_instance(cta, d, p, (int)(w / nparts), (int)(w % nparts), nparts, g, cterm, H, qv, ubar, dsafe, dsafe_obst,
+                              obst, P, q, A, bvec, lb, ub, sh);
         __syncthreads();
     }
 }
@@ -380,16 +390,18 @@ extern "C" int scpb200_assemble_dense(const scpb200_dims *d, const scpb200_param
     rc = dev_info(&di);
     if (rc) return rc;
     const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
-    const size_t smem = ((size_t)n * 2 + (size_t)mc * 2 + mc + (size_t)n * 2 + n + 16) * 8;
+    const size_t smem = ((size_t)SCP_ASM_ZBUF + (size_t)n * 2 + (size_t)mc * 2 + mc + (size_t)n * 2 + n + 16) * 8;
     if (smem > (size_t)di.smem_optin) return set_err(SCPB200_ERR_SIZE, "assemble: row data exceed shared memory");
     CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble, 256, smem));
     if (occ < 1) occ = 1;
+    const int nparts = mc >= 16 ? env_int("SCPB200_ASM_PARTS", 4) : 1;      // work items per instance (row ranges)
     long grid = (long)di.sms * occ;
-    if (grid > d->B) grid = d->B;
+    if (env_int("SCPB200_ASM_GRID_ITEMS", 0)) grid = (long)d->B * nparts;    // one CTA per work item: the hardware scheduler balances
+    if (grid > (long)d->B * nparts) grid = (long)d->B * nparts;
     k_assemble<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(*d, *p, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q,
-                                                               A, b, lb, ub);
+                                                               A, b, lb, ub, nparts);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

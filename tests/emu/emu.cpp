@@ -52,10 +52,12 @@ extern "C" int emu_assemble_dense(const scpb200_dims *d, const scpb200_params *p
 {
     Cta *cta = new_cta();
     const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
-    std::vector<double> sh((size_t)n * 5 + (size_t)mc * 3 + 16);
+    std::vector<double> sh((size_t)SCP_ASM_ZBUF + (size_t)n * 5 + (size_t)mc * 3 + 32);
+    const int nparts = mc >= 16 ? 4 : 1;
     for (int bi = 0; bi < d->B; ++bi)
-        scp_assemble_instance(*cta, *d, *p, bi, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, b, lb, ub,
-                              sh.data());
+        for (int part = 0; part < nparts; ++part)
+            scp_assemble_instance(*cta, *d, *p, bi, part, nparts, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, b,
+                                  lb, ub, sh.data());
     free(cta);
     return 0;
 }

@@ -313,3 +313,78 @@ def test_error_codes_not_exceptions_from_c(mods):
     lib.scpb200_default_params(C.byref(p))
     d = capi.Dims(1, 8, 10, 0, 2)
     assert lib.scpb200_mpc_setup(C.byref(d), C.byref(p), *([None] * 13)) == -1
+
+
+class _Model:
+    nx, nu, ny, is_noise = 6, 1, 2, False
+
+
+class _Scenario:
+    """The fields of the reference's Scenario object that the path reads, from a golden record."""
+
+    def __init__(self, G):
+        self.model = _Model()
+        self.nVeh, self.Hp, self.Hu, self.nObst = int(G["sc_nVeh"]), int(G["sc_Hp"]), int(G["sc_Hp"]), 0
+        self.dt, self.dsafeExtra = float(G["sc_dt"]), float(G["sc_dsafeExtra"])
+        self.tick_length, self.delay_x, self.delay_u = float(G["sc_tick_length"]), float(G["sc_delay_x"]), float(G["sc_delay_u"])
+        self.mechanicalSteeringLimit, self.duLim = float(G["sc_mechanicalSteeringLimit"]), float(G["sc_duLim"])
+        self.Lf, self.Lr, self.Q, self.Q_final, self.R = (list(G[k]) for k in ("sc_Lf", "sc_Lr", "sc_Q", "sc_Q_final", "sc_R"))
+        self.referenceTrajectories = [p for p in G["sc_poly"]]
+        self.dsafeVehicles = G["sc_dsafeVehicles"]
+        self.obstacles, self.dsafeObstacles = [], np.zeros((self.nVeh, 0))
+
+
+def test_reference_call_surface_closed_loop(mods):
+    """main.py:123-134 with the drop-in classes, fed the reference's own measured states for all 50 MPC steps of
+    the default run: IterClass (delay compensation + reference sampling), SCPcontroller(...).SCP_controller(Iter),
+    warm-started from the previous controllerOutput exactly as main.py does."""
+    facade_iter = importlib.import_module(PKG + ".MPC_Iter")
+    facade_scp = importlib.import_module(PKG + ".SCP_controller")
+    R = load_golden("circle8_hp10_run.npz")
+    sc = _Scenario(load_golden("circle8_hp10_step0.npz"))
+    outputs = []
+    nsteps = R["x_measured"].shape[0]
+    for i in range(nsteps):
+        Iter = facade_iter.IterClass(sc, R["x_measured"][i], R["u_path"][i], np.zeros((0, 2)), np.full((1, sc.nVeh), sc.mechanicalSteeringLimit))
+        assert np.abs(Iter.x0 - R["x0"][i]).max() < 1e-7                        # the reference's LSODA is ~1e-8
+        assert np.abs(Iter.ReferenceTrajectoryPoints - R["RefPts"][i]).max() < 1e-6
+        # teacher-forced warm start: the reference's previous solution (the SCP map amplifies 1e-14 at symmetric steps)
+        prev = [] if i == 0 else {"u": R["u_final"][i - 1].reshape(-1, 1)}
+        ctl = facade_scp.SCPcontroller(sc, Iter, prev)
+        U, traj, out = ctl.SCP_controller(Iter)
+        outputs.append(out)
+        assert U.shape == (sc.Hp, sc.nVeh) and traj.shape == (sc.Hp, 2, sc.nVeh) and out["u"].shape == (sc.nVeh * sc.Hp, 1)
+        if R["scp_iters"][i] <= 5:
+            assert len(out["optimization_log"]["slack"]) == R["scp_iters"][i]
+            assert np.abs(out["u"].ravel() - R["u_final"][i]).max() < 2e-6
+            assert np.abs(traj - R["Traj"][i]).max() < 1e-4
+        feas = ctl.QCQP_evaluate(out["u"])[0]
+        assert feas == bool(R["feasible_last"][i])
+        evo = ctl.evaluateInOriginalProblem(U, traj, {"ignoreQCQPcheck": True})
+        if R["scp_iters"][i] <= 5:
+            # evaluations_obj_value is computed by the reference on the CLAMPED U (main.py:164-174, :202)
+            evc = ctl.evaluateInOriginalProblem(R["U_clamped"][i], R["Traj"][i], {})
+            assert abs(evc["predictionObjectiveValue"] - R["evaluations_obj_value"][i]) <= 1e-6 * max(1.0, abs(R["evaluations_obj_value"][i]))
+        assert "constraintValuesVehicle" in evo
+    assert sum(len(o["optimization_log"]["slack"]) for o in outputs) in range(120, 129)      # 124 QPs in the reference run
+
+
+def test_mpcclass_attributes_match_reference(mods):
+    facade_iter = importlib.import_module(PKG + ".MPC_Iter")
+    G = load_golden("circle8_hp10_step10.npz")
+    sc = _Scenario(G)
+
+    class _It:
+        pass
+    It = _It()
+    It.x0, It.u0 = G["x0"], G["u0"]
+    mpc = facade_iter.MPCclass(sc, It)
+    for name, ref in (("Mathcal_A", G["Mathcal_A"]), ("Mathcal_B", G["Mathcal_B"]), ("Phi_0", G["Phi_0"])):
+        got = getattr(mpc, name)
+        assert got.shape == ref.shape, name
+        assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max(), name
+    assert np.abs(mpc.Mathcal_C[:, 0, :] - G["Mathcal_C"]).max() <= 1e-11 * np.abs(G["Mathcal_C"]).max()
+    assert np.abs(mpc.const_term[:, 0, :] - G["const_term"]).max() <= 1e-11 * np.abs(G["const_term"]).max()
+    assert np.abs(mpc.gamma_0[0] - G["gamma_0"]).max() <= 1e-9 * max(1.0, np.abs(G["gamma_0"]).max())
+    assert np.abs(mpc.A[:, :, 0, :] - G["A"]).max() < 1e-12 and mpc.A.shape == (6, 6, sc.Hp, sc.nVeh)
+    assert np.abs(mpc.B[:, 0, 3, :] - G["B"]).max() < 1e-12 and np.abs(mpc.E[:, 5, :] - G["E"]).max() < 1e-12
