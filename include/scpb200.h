@@ -186,6 +186,22 @@ int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p, const doub
                       double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
                       double *max_violation, void *ws, void *stream);
 
+/*
+ * Scheduling extension (no reference counterpart: the reference solves one scenario at a time).  The SCP / interior-
+ * point iteration counts vary by 10x between instances, so the order in which the persistent CTAs pull instances
+ * decides how long the batch waits for its last straggler.
+ *   scpb200_work_order       order[B] int32 = instance indices sorted by descending work[B] int32 (e.g. the previous MPC
+ *                            step's ipm_iters of the same instances); device arrays.
+ *   scpb200_scp_solve_ordered  as scpb200_scp_solve, pulling instances in `order` (NULL = natural order).
+ * Results are independent of the order (instances are independent).
+ */
+int scpb200_work_order(int32_t B, const int32_t *work, int32_t *order, void *stream);
+int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                              const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                              const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                              double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                              double *max_violation, const int32_t *order, void *ws, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

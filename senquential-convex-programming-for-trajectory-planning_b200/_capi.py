@@ -63,6 +63,8 @@ PROTOTYPES = {
     "scpb200_advance_linear": [C.POINTER(Dims), _P, _P, C.c_double, C.c_double, _P, _P, _P],
     "scpb200_qp_solve_dense": [C.POINTER(Dims), C.POINTER(Params), C.c_int32, C.c_int32] + [_P] * 13,
     "scpb200_scp_solve": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 19,
+    "scpb200_scp_solve_ordered": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 20,
+    "scpb200_work_order": [C.c_int32, _P, _P, _P],
 }
 
 _lib = None

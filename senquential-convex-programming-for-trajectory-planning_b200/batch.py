@@ -84,7 +84,12 @@ class BatchSCP:
             nbytes = C.c_size_t(0)
             check(self.lib.scpb200_workspace_bytes(C.byref(self.dims), C.byref(nbytes)), "scpb200_workspace_bytes")
             self.ws = torch.zeros(max(int(nbytes.value), 256), dtype=torch.uint8, device=self.device)
+            self.order = torch.zeros(B_, **i32)
         self.kernel_launches = 0
+        #: pull the work queue in descending order of the previous solve's interior-point iteration counts
+        #: (longest-processing-time-first).  Scheduling only: results do not depend on it.
+        self.schedule_by_previous_work = True
+        self._have_work = False
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -123,13 +128,20 @@ class BatchSCP:
     def solve(self):
         """K4: SCPcontroller.SCP_controller (SCP_controller.py:40-197) for the whole batch; u is warm start and result."""
         with torch.cuda.device(self.device):
-            check(self.lib.scpb200_scp_solve(
+            order = None
+            if self.schedule_by_previous_work and self._have_work and self.B > 1:
+                check(self.lib.scpb200_work_order(self.B, _ptr(self.ipm_iters), _ptr(self.order), self._stream()),
+                      "scpb200_work_order")
+                self.kernel_launches += 1
+                order = self.order
+            check(self.lib.scpb200_scp_solve_ordered(
                 C.byref(self.dims), C.byref(self.params), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv),
                 _ptr(self.gamma0), _ptr(self.dsafe), _ptr(self.dsafe_obst), _ptr(self.obst), _ptr(self.u),
                 _ptr(self.traj), _ptr(self.U), _ptr(self.log), _ptr(self.scp_iters), _ptr(self.ipm_iters),
-                _ptr(self.status), _ptr(self.obj), _ptr(self.max_violation), _ptr(self.ws), self._stream()),
-                "scpb200_scp_solve")
-        self.kernel_launches += 1
+                _ptr(self.status), _ptr(self.obj), _ptr(self.max_violation), _ptr(order), _ptr(self.ws), self._stream()),
+                "scpb200_scp_solve_ordered")
+        self.kernel_launches += 2          # k_queue_init + k_scp_solve
+        self._have_work = True
 
     def controller_step(self):
         """The controller stage of one MPC step: K1 then K4 (what main.py:131-134 does per step)."""

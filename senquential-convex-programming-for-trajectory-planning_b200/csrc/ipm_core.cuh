@@ -59,7 +59,7 @@ struct IpmResult {
 // ------------------------------------------------------------------------------------------------ 8x8 tile leaves
 // All 8x8 tiles (normal matrix, scratch) use the half-row-swapped layout of scp_tphys().
 //
-// Cholesky factor of one diagonal tile, in place (lower triangle; the upper triangle is zeroed), reciprocal
+// Cholesky factor of one diagonal tile, in place (lower triangle only), reciprocal
 // pivots to dinv[0..8).  The factorisation is ONE dependent chain of 8 pivots (rsqrt 63 + mul 9 + fma 9 cycles
 // each on B200), so a single lane runs it out of registers with every other update off the chain.
 #define SCP_TRI(r, c) ((r) * ((r) + 1) / 2 + (c))
@@ -92,7 +92,7 @@ SCP_FN void tile_potrf(double *Tkk, double *dinv, int *fixed)
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) Tkk[scp_tphys(r, c)] = (c <= r) ? a[SCP_TRI(r, c)] : 0.0;
+        for (int c = 0; c <= r; ++c) Tkk[scp_tphys(r, c)] = a[SCP_TRI(r, c)];     // the upper triangle is never read
     if (bad) *fixed = 1;
 }
 
@@ -210,14 +210,16 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
 {
     const int T = m.T;
     double *S = m.S, *dinv = m.dinv, *wbuf = m.wbuf;
-    for (int K = 0; K < T; ++K) {
-        double *Lkk = S + scp_tile_off(K, K);
-        CTA_PHASE(tid)
-            if (tid == 0) tile_potrf(Lkk, dinv + K * 8, fixed);
-        CTA_PHASE_END
-        SCP_TIMER(2)
+    // Look-ahead: the factorisation of diagonal tile K+1 (a single-lane dependency chain, ~1.7 k cycles) runs in
+    // warp 0 during the trailing update of step K, right after that warp has updated the tile; the other warps
+    // carry the remaining tiles of the update.
+    CTA_PHASE(tid)
+        if (tid == 0) tile_potrf(S + scp_tile_off(0, 0), dinv, fixed);
+    CTA_PHASE_END
+    SCP_TIMER(2)
+    for (int K = 0; K < T - 1; ++K) {
+        const double *Lkk = S + scp_tile_off(K, K);
         const int Tr = T - K - 1;
-        if (Tr == 0) break;
         // (b) panel rows: x L_KK' = s  ->  x[c] = (s[c] - sum_{c2<c} x[c2] L[c][c2]) dinv[c]
         CTA_PHASE(tid)
             for (int pr = tid; pr < Tr * 8; pr += cta.nt) {
@@ -240,15 +242,24 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
             }
         CTA_PHASE_END
         SCP_TIMER(3)
-        // (c) trailing update: S_IJ -= L_IK L_JK'   (K < J <= I), one warp per output tile
+        // (c) trailing update: S_IJ -= L_IK L_JK'   (K < J <= I), one warp per output tile; tile index 0 is the next
+        // diagonal tile: warp 0 takes it first and factors it while the others work through the rest
         WARP_SECTION(w, nw)
+            const int ntile = Tr * (Tr + 1) >> 1;
             WARP_PHASE(lane)
-                const int ntile = Tr * (Tr + 1) >> 1;
-                for (int t = w; t < ntile; t += nw) {
-                    int ii, jj;
-                    scp_tri_decode(t, &ii, &jj);
-                    warp_tile_syrk(lane, S + scp_tile_off(K + 1 + ii, K + 1 + jj), S + scp_tile_off(K + 1 + ii, K),
-                                   S + scp_tile_off(K + 1 + jj, K));
+                if (w == 0) warp_tile_syrk(lane, S + scp_tile_off(K + 1, K + 1), S + scp_tile_off(K + 1, K), S + scp_tile_off(K + 1, K));
+            WARP_PHASE_END
+            WARP_PHASE(lane)
+                if (w == 0 && lane == 0) tile_potrf(S + scp_tile_off(K + 1, K + 1), dinv + (K + 1) * 8, fixed);
+                if (w > 0 || nw == 1) {
+                    // tiles 1 .. ntile-1 over warps 1 .. nw-1 (a single-warp CTA does them itself), (ii, jj) advanced incrementally
+                    const int nwork = nw > 1 ? nw - 1 : 1;
+                    int ii = 0, jj = nw > 1 ? w : 1;
+                    for (int t = jj; t < ntile; t += nwork, jj += nwork) {
+                        while (jj > ii) { jj -= ii + 1; ++ii; }
+                        warp_tile_syrk(lane, S + scp_tile_off(K + 1 + ii, K + 1 + jj), S + scp_tile_off(K + 1 + ii, K),
+                                       S + scp_tile_off(K + 1 + jj, K));
+                    }
                 }
             WARP_PHASE_END
         WARP_SECTION_END

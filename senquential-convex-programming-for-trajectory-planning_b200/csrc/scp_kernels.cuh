@@ -633,10 +633,24 @@ struct ScpIO {
     const double *g, *cterm, *H, *qv, *gamma0, *dsafe, *dsafe_obst, *obst;   // batch base pointers
     double *u, *traj, *U, *log, *obj, *max_violation;
     int32_t *scp_iters, *ipm_iters, *status;
+    // Preemption (work-queue scheduling at QP granularity): with `state` non-null an invocation runs at most `quantum`
+    // SCP iterations of the instance, then parks it (u in io.u, the loop scalars in state[b]) for a later invocation
+    // by any CTA.  The arithmetic is that of the uninterrupted loop, so results are bit-identical.
+    double *state;      // [B][SCP_STATE_W] or null (run to completion)
+    int quantum;
 };
+#define SCP_STATE_W 6   /* obj0, mv0, it, ipm_total, status bits, pinned (never parked) */
+
+// loads of data another CTA may have written during this launch (parked instances) must bypass L1
+#if SCP_DEVICE_BUILD
+#define SCP_LD_COHERENT(ptr) __ldcg(ptr)
+#else
+#define SCP_LD_COHERENT(ptr) (*(ptr))
+#endif
 
 // SCP_optimizer (SCP_controller.py:74-197) + the result shaping of SCP_controller (:68-70) for instance b.
-SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const ScpIO &io,
+// Returns true when the instance is finished (results written), false when it was parked.
+SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const ScpIO &io,
                                ScpMem &s)
 {
     const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp;
@@ -660,6 +674,9 @@ SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     op.xom = 0.0; op.wsum = 0.0;
     op.Msm = s.Msm; op.alpha = s.alpha; op.alpha_slots = s.alpha_slots; op.alpha_stride = s.alpha_stride;
 
+    double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
+    const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance
+
     // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
     CTA_PHASE(tid)
         for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = gB[e];
@@ -668,8 +685,8 @@ SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         for (int c = tid; c < m.n1p; c += cta.nt) {
             double uv = 0.0;
             if (c < n) {
-                uv = uB[c];
-                if (c == 0 && fabs(uv) < 2.220446049250313e-16) uv = 2.220446049250313e-16;
+                uv = SCP_LD_COHERENT(uB + c);
+                if (c == 0 && it_resume == 0 && fabs(uv) < 2.220446049250313e-16) uv = 2.220446049250313e-16;
             }
             s.ucur[c] = uv;
             m.q[c] = (c < n) ? qB[c] : (c == n ? p.omega_weight : 0.0);
@@ -677,11 +694,27 @@ SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     CTA_PHASE_END
 
     ScpEval ev;
-    scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra, p.constraint_tol,
-                 p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
-    double obj0 = ev.obj, mv0 = ev.max_violation;
+    double obj0, mv0;
     int it = 0, ipm_total = 0, st = 0, stopped = 0;
-    for (it = 0; it < p.max_scp_iter; ++it) {
+    if (it_resume == 0) {
+        scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra, p.constraint_tol,
+                     p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
+        obj0 = ev.obj; mv0 = ev.max_violation;
+    } else {
+        obj0 = SCP_LD_COHERENT(stB + 0); mv0 = SCP_LD_COHERENT(stB + 1);
+        it = it_resume; ipm_total = (int)SCP_LD_COHERENT(stB + 3); st = (int)SCP_LD_COHERENT(stB + 4);
+        ev.obj = obj0; ev.max_violation = mv0; ev.sum_violations = 0.0; ev.feasible = mv0 > 0.0 ? 0 : 1;
+    }
+    const int it_park = (stB && stB[5] == 0.0) ? it + (io.quantum > 0 ? io.quantum : 1) : p.max_scp_iter;
+    for (; it < p.max_scp_iter; ++it) {
+        if (it >= it_park) {
+            // park: u and the loop scalars go back to global memory; another invocation continues from here
+            CTA_PHASE(tid)
+                for (int c = tid; c < n; c += cta.nt) uB[c] = s.ucur[c];
+                if (tid == 0) { stB[0] = obj0; stB[1] = mv0; stB[2] = (double)it; stB[3] = (double)ipm_total; stB[4] = (double)st; }
+            CTA_PHASE_END
+            return false;
+        }
         scp_linearise(cta, nVeh, Hp, nObst, s.g, cB, s.ucur, dsB, dsoB, obB, p.dsafeExtra, s.resp, s.dbar, m.bA);
         CTA_PHASE(tid)
             for (int c = tid; c < m.n1p; c += cta.nt) {
@@ -747,6 +780,7 @@ SCP_FN void scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             if (io.max_violation) io.max_violation[b] = ev.max_violation;
         }
     CTA_PHASE_END
+    return true;
 }
 
 // ================================================================================================ K3: dense QP

@@ -201,9 +201,60 @@ __device__ __forceinline__ int next_instance(int *counter, int *slot)
     return *slot;
 }
 
+// ---- work queue of the SCP kernel -------------------------------------------------------------------------------
+// The unit of scheduling is ONE QP (one SCP iteration of one instance), not one instance: instances need between 1 and
+// max_scp_iter QPs, so with instance-granular scheduling a 1024-instance step waits for stragglers that started late.
+// A bounded FIFO ring in the workspace holds the instances that still have work; a CTA pops one, runs `quantum` SCP
+// iterations, and either finishes it or parks it (u + five scalars) and pushes it back at the tail.  Every live
+// instance therefore advances round-robin and the CTAs stay busy until the last QP of the step.
+//   hdr[0] = head ticket, hdr[1] = tail ticket, hdr[2] = instances not yet finished; slots[cap], cap = power of two
+//   >= 2B, empty = -1.  Pop ticket h is served by push ticket h (FIFO); a popper whose ticket is never served leaves
+//   when hdr[2] reaches 0.
+struct WorkQueue {
+    int *hdr, *slots;
+    int cap;
+};
+
+__device__ __forceinline__ void queue_push(const WorkQueue &q, int b)
+{
+    const int t = atomicAdd(q.hdr + 1, 1);
+    int *p = q.slots + (t & (q.cap - 1));
+    while (atomicCAS(p, -1, b) != -1) __nanosleep(64);
+}
+
+// called by thread 0; returns an instance index, or -1 when every instance has finished
+__device__ __forceinline__ int queue_pop(const WorkQueue &q)
+{
+    const int h = atomicAdd(q.hdr, 1);
+    int *p = q.slots + (h & (q.cap - 1));
+    unsigned ns = 32;
+    for (;;) {
+        const int v = atomicExch(p, -1);
+        if (v >= 0) return v;
+        if (*(volatile int *)(q.hdr + 2) <= 0) return -1;
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+    }
+}
+
+// `order` (optional) lists the instances by descending expected work.  The first `npinned` of them are the likely
+// stragglers: they are started first and never parked, so the longest chain of QPs of the step runs without waiting;
+// everything else shares the remaining CTAs round-robin.
+__global__ void k_queue_init(int B, const int32_t *order, int npinned, WorkQueue q, double *state)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < q.cap) q.slots[i] = i < B ? (order ? order[i] : i) : -1;
+    if (i < B) {
+        const int b = order ? order[i] : i;
+        state[(size_t)b * SCP_STATE_W + 2] = 0.0;                  // it = 0: a fresh instance
+        state[(size_t)b * SCP_STATE_W + 5] = (order && i < npinned) ? 1.0 : 0.0;
+    }
+    if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
+}
+
 template <bool ALL_SHARED>
 __global__ void __launch_bounds__(SCP_MAX_THREADS, SCP_MIN_CTAS)
-k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, int *counter, double *gws, size_t gl_stride, size_t sh_lim,
+k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws, size_t gl_stride, size_t sh_lim,
             int alpha_slots, int want_H)
 {
     extern __shared__ double sh[];
@@ -212,8 +263,61 @@ k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, int *counter, double *gw
     ScpBump bp = scp_bump(sh, sh_lim, ALL_SHARED ? (double *)0 : gws + (size_t)blockIdx.x * gl_stride, ALL_SHARED);
     ScpMem s;
     scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H);
-    for (int b = next_instance(counter, &slot); b < d.B; b = next_instance(counter, &slot))
-        scp_solve_instance(cta, d, p, b, io, s);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const int b = queue_pop(q);
+            __threadfence();                       // acquire: the parked state written by the CTA that pushed b
+            slot = b;
+        }
+        __syncthreads();
+        const int b = slot;
+        if (b < 0) break;
+        const bool done = scp_solve_instance(cta, d, p, b, io, s);
+        __threadfence();                           // release: every thread's writes of this invocation ...
+        __syncthreads();                           // ... are ordered before thread 0 hands the instance on
+        if (threadIdx.x == 0) {
+            if (done) atomicSub(q.hdr + 2, 1);
+            else queue_push(q, b);
+        }
+    }
+}
+
+// Pull order for the work queue: instances sorted by DEscending expected work (longest-processing-time-first), so
+// that the instances with the most interior-point iterations start first and the step does not end on a straggler.
+// Counting sort by key = min(work, ORDER_BINS-1) in one CTA; ties keep no particular order (scheduling only).
+#define ORDER_BINS 2048
+__global__ void __launch_bounds__(1024) k_work_order(int B, const int32_t *work, int32_t *order)
+{
+    __shared__ int hist[ORDER_BINS];
+    __shared__ int part[1024];
+    const int t = (int)threadIdx.x;
+    for (int i = t; i < ORDER_BINS; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (int i = t; i < B; i += 1024) {
+        int k = work[i];
+        k = k < 0 ? 0 : (k >= ORDER_BINS ? ORDER_BINS - 1 : k);
+        atomicAdd(&hist[ORDER_BINS - 1 - k], 1);              // bin 0 = most work
+    }
+    __syncthreads();
+    const int per = ORDER_BINS / 1024;
+    int loc = 0;
+    for (int j = 0; j < per; ++j) loc += hist[t * per + j];
+    part[t] = loc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {               // inclusive scan of the per-thread sums
+        const int v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int base = part[t] - loc;
+    for (int j = 0; j < per; ++j) { const int c = hist[t * per + j]; hist[t * per + j] = base; base += c; }
+    __syncthreads();
+    for (int i = t; i < B; i += 1024) {
+        int k = work[i];
+        k = k < 0 ? 0 : (k >= ORDER_BINS ? ORDER_BINS - 1 : k);
+        order[atomicAdd(&hist[ORDER_BINS - 1 - k], 1)] = i;
+    }
 }
 
 template <bool ALL_SHARED>
@@ -239,6 +343,18 @@ struct SolvePlan {
 };
 
 #define WS_HEADER 256
+static size_t queue_cap(long B)
+{
+    size_t c = 64;
+    while (c < (size_t)2 * (size_t)(B < 1 ? 1 : B)) c <<= 1;
+    return c;
+}
+// bytes of the per-call scheduling area that follows the header: ring slots + parked-instance state
+static size_t queue_bytes(long B)
+{
+    const size_t b = queue_cap(B) * sizeof(int) + (size_t)(B < 1 ? 1 : B) * SCP_STATE_W * sizeof(double);
+    return (b + 255) & ~(size_t)255;
+}
 #define SCP_SM_SHARED_BYTES 233472      /* 228 KiB per SM on B200, 1 KiB reserved per resident CTA */
 
 // Pick the occupancy target: the largest number of CTAs per SM (<= max_ctas) for which the whole working set is
@@ -339,7 +455,7 @@ extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
     const int n1 = d->nVeh * d->Hp + 1, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
     rc = plan_qp(n1, mc, 1 << 30, &b);
     if (rc) return rc;
-    *bytes = a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes;
+    *bytes = (a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes) + queue_bytes(d->B);
     return 0;
 }
 
@@ -499,11 +615,31 @@ extern "C" int scpb200_qp_solve_dense(const scpb200_dims *d, const scpb200_param
     return 0;
 }
 
+extern "C" int scpb200_work_order(int32_t B, const int32_t *work, int32_t *order, void *stream)
+{
+    if (B < 0 || (B && (!work || !order))) return set_err(SCPB200_ERR_ARG, "scpb200_work_order: bad argument");
+    if (B == 0) return 0;
+    k_work_order<<<1, 1024, 0, (cudaStream_t)stream>>>(B, work, order);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
                                  const double *H, const double *qv, const double *gamma0, const double *dsafe,
                                  const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
                                  double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
                                  double *max_violation, void *ws, void *stream)
+{
+    return scpb200_scp_solve_ordered(d, p, g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, scp_iters,
+                                     ipm_iters, status, obj, max_violation, (const int32_t *)0, ws, stream);
+}
+
+extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_params *p, const double *g,
+                                         const double *cterm, const double *H, const double *qv, const double *gamma0,
+                                         const double *dsafe, const double *dsafe_obst, const double *obst,
+                                         double *u_inout, double *traj, double *U, double *log, int32_t *scp_iters,
+                                         int32_t *ipm_iters, int32_t *status, double *obj, double *max_violation,
+                                         const int32_t *order, void *ws, void *stream)
 {
     int rc = check_dims(d);
     if (rc) return rc;
@@ -518,14 +654,20 @@ extern "C" int scpb200_scp_solve(const scpb200_dims *d, const scpb200_params *p,
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
-    int *counter = (int *)ws;
-    double *gws = (double *)((char *)ws + WS_HEADER);
+    WorkQueue q;
+    q.hdr = (int *)ws;
+    q.cap = (int)queue_cap(d->B);
+    q.slots = (int *)((char *)ws + WS_HEADER);
+    io.state = (double *)((char *)ws + WS_HEADER + (size_t)q.cap * sizeof(int));
+    io.quantum = env_int("SCPB200_QUANTUM", 1);
+    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
+    k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2), q, io.state);
+    CUDA_TRY(cudaGetLastError());
     if (pl.all_shared)
-        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, gws, pl.gl_stride, pl.sh_lim,
+        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, q, gws, pl.gl_stride, pl.sh_lim,
                                                                      pl.alpha_slots, pl.want_H);
     else
-        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, counter, gws, pl.gl_stride, pl.sh_lim,
+        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, q, gws, pl.gl_stride, pl.sh_lim,
                                                                       pl.alpha_slots, pl.want_H);
     CUDA_TRY(cudaGetLastError());
     return 0;

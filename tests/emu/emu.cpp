@@ -123,7 +123,21 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
     scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1);
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
-    for (int b = 0; b < d->B; ++b) scp_solve_instance(*cta, *d, *p, b, io, s);
+    // SCPB200_EMU_QUANTUM=q: exercise the park / resume path of the work-queue scheduler (q SCP iterations per
+    // invocation, round-robin over the live instances as the device FIFO does)
+    const char *qe = getenv("SCPB200_EMU_QUANTUM");
+    if (qe && atoi(qe) > 0) {
+        io.quantum = atoi(qe);
+        io.state = (double *)calloc((size_t)d->B * SCP_STATE_W, sizeof(double));
+        char *done = (char *)calloc(d->B, 1);
+        for (int live = d->B; live > 0;)
+            for (int b = 0; b < d->B; ++b)
+                if (!done[b] && scp_solve_instance(*cta, *d, *p, b, io, s)) { done[b] = 1; --live; }
+        free(done);
+        free(io.state);
+    } else {
+        for (int b = 0; b < d->B; ++b) scp_solve_instance(*cta, *d, *p, b, io, s);
+    }
     free(cta);
     return 0;
 }

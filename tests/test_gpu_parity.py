@@ -266,6 +266,36 @@ def test_results_do_not_depend_on_batch_position(mods):
     np.testing.assert_array_equal(u_a[48:], u_c)
 
 
+def test_work_order_and_ordered_solve(mods):
+    """scpb200_work_order gives a permutation sorted by descending work; the ordered solve (longest instances first)
+    returns bit-identical results to the natural pull order."""
+    torch, scen = mods["torch"], mods["scen"]
+    lib = mods["capi"].load()
+    rng = np.random.default_rng(3)
+    for B in (1, 7, 1024, 5000):
+        work = torch.as_tensor(rng.integers(0, 3000, B).astype(np.int32)).cuda()
+        order = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+        assert lib.scpb200_work_order(B, C.c_void_p(work.data_ptr()), C.c_void_p(order.data_ptr()), None) == 0
+        o = host(order).astype(np.int64)
+        assert sorted(o.tolist()) == list(range(B))
+        w = np.minimum(host(work)[o], 2047)
+        assert (np.diff(w) <= 0).all()
+    cb = scen.circle_batch(300, step_lo=5, step_hi=7)
+    def run(flag):
+        bs = mods["batch"].BatchSCP(300, 8, 10)
+        bs.schedule_by_previous_work = flag
+        bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((300, 80)))
+        out = []
+        for _ in range(2):
+            bs.controller_step()
+            out.append((host(bs.u).copy(), host(bs.scp_iters).copy(), host(bs.ipm_iters).copy()))
+            bs.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+        return out
+    for a, b in zip(run(True), run(False)):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+
+
 def test_ode_predict_and_linear_advance(mods, oracle):
     G = load_golden("circle8_hp10_step10.npz")
     torch = mods["torch"]

@@ -212,3 +212,19 @@ def test_scp_kernel_free_running(oracle, fname):
     else:
         assert abs(int(r["scp_iters"][0]) - int(G["scp_iters"])) <= 2
     assert (r["status"][0] & (capi.ST_SCP_MAXITER | capi.ST_INFEASIBLE)) == 0
+
+
+@pytest.mark.parametrize("quantum", [1, 3])
+def test_scp_kernel_park_and_resume_is_bit_identical(oracle, quantum, monkeypatch):
+    """The work-queue scheduler runs an instance `quantum` SCP iterations at a time and parks it in between (u + five
+    scalars in global memory).  The parked / resumed run must reproduce the uninterrupted one bit for bit."""
+    G = load_golden("circle8_hp10_step6.npz")        # 12 SCP iterations in the reference's run
+    S = _setup(oracle, G)
+    args = (S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], G["u_warm"][None], params_for(G))
+    monkeypatch.delenv("SCPB200_EMU_QUANTUM", raising=False)
+    a = emu.scp_solve(*args)
+    monkeypatch.setenv("SCPB200_EMU_QUANTUM", str(quantum))
+    b = emu.scp_solve(*args)
+    assert a["scp_iters"][0] > quantum
+    for k in ("u", "traj", "U", "log", "scp_iters", "ipm_iters", "status", "obj", "max_violation"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
