@@ -117,7 +117,7 @@ SCP_FN void tile_trtri_column(const double *L, const double *dinv, int j, double
 #if SCP_DEVICE_BUILD
 SCP_FN void scp_dmma(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 SCP_FN int scp_frag_rowmajor(int lane, int h)     // element (row = lane>>2, col = (lane&3) + 4h)
@@ -417,7 +417,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         }
     CTA_PHASE_END
     SCP_TIMER(0)
-    op.form_normal(cta, m, m.dsA, m.tn);
+    op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
     op.prep(cta, (const double *)0, m.bA);
     CTA_PHASE(tid)
         for (int c = tid; c < n1; c += cta.nt) {
@@ -538,7 +538,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                 m.tn[c] = d;
             }
         CTA_PHASE_END
-        op.form_normal(cta, m, m.dsA, m.tn);
+        op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
         SCP_TIMER(1)
         chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
 

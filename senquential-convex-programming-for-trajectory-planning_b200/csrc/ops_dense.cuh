@@ -40,7 +40,7 @@ struct DenseOp {
 
     // S(lower) = P + A' diag(dd) A + diag(dg): clear, then accumulate
     template <class Mem>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg)
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg SCP_TIMER_ARG)
     {
         CTA_PHASE(tid)
             const int tot = (m.T * (m.T + 1) >> 1) * SCP_TILE2;

@@ -23,9 +23,7 @@ struct PairOp {
     double xom, wsum;     // omega component of x / sum of w of the last prep
     double *red;          // reduction scratch
     double *Msm;          // [n][3] scratch: per (vehicle, step) sum of 4 dd dbar dbar' (xx, xy, yy)
-    double *alpha;        // per-warp scratch for the pair-block products, alpha_slots x alpha_stride doubles
-    int alpha_slots;      // 0: no scratch (large Hp) -> off-diagonal blocks are formed entry by entry
-    int alpha_stride;     // 2 * Hp(Hp+1)/2
+    int alpha_slots;      // pair-block mode: > 0 tensor path (pair_block_mma, Hp <= 64), 0 entry by entry
 
     SCP_MFN int pair_index(int i, int j) const { return i * nVeh - (i * (i + 1) >> 1) + (j - i - 1); }
 
@@ -133,18 +131,86 @@ struct PairOp {
         return 2.0 * (dbar[r * 2] * gv[l * 2] + dbar[r * 2 + 1] * gv[l * 2 + 1]);
     }
 
+    // One pair block on the FP64 tensor path, operands generated in registers (no scratch, no intra-warp exchange):
+    //     S[(j,b),(i,a)] = -sum_k cj[k][b] (dd_r ci[k][a]),   cv[k][l] = 2 dbar_r . g_v[k-l]  (l <= k, else 0),  r = r0 + k
+    // i.e. C = -Aj' (D Ai) with Hp x Hp causal factors.  Per m8n8k4 step lane l supplies A[row b = l>>2][col k = l&3] and
+    // B[row k = l&3][col a = l>>2] and owns C[b = l>>2][a = 2(l&3), 2(l&3)+1].  Causality (k >= max(a, b)) skips the
+    // k-steps below the tile diagonal: Hp = 10 needs 6 DMMAs per pair.
+#define SCP_PAIR_NA 8      /* a-tiles held in accumulators: Hp <= 64 */
+    SCP_MFN void pair_block_mma(int lane, double *S, int i, int j, int r0, const double *dd) const
+    {
+        const int nt = (Hp + 7) >> 3;
+        if (nt <= 2) pair_block_mma_n<2>(lane, S, i, j, r0, dd);          // the unrolled a-tile loop matches the horizon
+        else if (nt <= 4) pair_block_mma_n<4>(lane, S, i, j, r0, dd);
+        else pair_block_mma_n<SCP_PAIR_NA>(lane, S, i, j, r0, dd);
+    }
+    template <int NA>
+    SCP_MFN void pair_block_mma_n(int lane, double *S, int i, int j, int r0, const double *dd) const
+    {
+        const double *gi = g + (size_t)i * Hp * 2, *gj = g + (size_t)j * Hp * 2;
+#if SCP_DEVICE_BUILD
+        const double2 *__restrict__ gi2 = reinterpret_cast<const double2 *>(gi);
+        const double2 *__restrict__ gj2 = reinterpret_cast<const double2 *>(gj);
+        const double2 *__restrict__ db2 = reinterpret_cast<const double2 *>(dbar) + r0;
+        const double *__restrict__ ddr = dd + r0;
+        const int q = lane >> 2, kq = lane & 3;
+        const int nt = (Hp + 7) >> 3, nk = (Hp + 3) >> 2;
+        for (int tb = 0; tb < nt; ++tb) {
+            double acc[NA][2];
+#pragma unroll
+            for (int ta = 0; ta < NA; ++ta) acc[ta][0] = acc[ta][1] = 0.0;
+            const int b = 8 * tb + q;
+            for (int s = 2 * tb; s < nk; ++s) {
+                const int k = 4 * s + kq;
+                double dxk = 0.0, dyk = 0.0, ddk = 0.0;
+                if (k < Hp) { const double2 t = db2[k]; dxk = 2.0 * t.x; dyk = 2.0 * t.y; ddk = ddr[k]; }
+                double ae = 0.0;
+                if (k < Hp && b <= k) { const double2 t = gj2[k - b]; ae = dxk * t.x + dyk * t.y; }
+                dxk *= ddk; dyk *= ddk;
+#pragma unroll
+                for (int ta = 0; ta < NA; ++ta)
+                    if (ta < nt && 2 * ta <= s) {                       // warp-uniform
+                        const int a = 8 * ta + q;
+                        double be = 0.0;
+                        if (k < Hp && a <= k) { const double2 t = gi2[k - a]; be = dxk * t.x + dyk * t.y; }
+                        scp_dmma(acc[ta][0], acc[ta][1], ae, be);
+                    }
+            }
+            if (b < Hp) {
+#pragma unroll
+                for (int ta = 0; ta < NA; ++ta)
+                    if (ta < nt) {
+                        const int a0 = 8 * ta + 2 * kq;
+                        if (a0 < Hp) S[scp_sidx(j * Hp + b, i * Hp + a0)] = -acc[ta][0];
+                        if (a0 + 1 < Hp) S[scp_sidx(j * Hp + b, i * Hp + a0 + 1)] = -acc[ta][1];
+                    }
+            }
+        }
+#else
+        if (lane == 0)
+            for (int b = 0; b < Hp; ++b)
+                for (int a = 0; a < Hp; ++a) {
+                    double acc = 0.0;
+                    for (int k = (a > b ? a : b); k < Hp; ++k)
+                        acc += coef2(gj, r0 + k, k - b) * (dd[r0 + k] * coef2(gi, r0 + k, k - a));
+                    S[scp_sidx(j * Hp + b, i * Hp + a)] = -acc;
+                }
+#endif
+    }
+
     // S(lower) = blkdiag(2H, 0) + A' diag(dd) A + diag(dg), every entry written exactly once (no clear, no
     // read-modify-write):
     //   diagonal blocks   S[(v,a),(v,b)] = 2H_v[a][b] + dg + sum_{k>=a} g_v[k-a]' M_v(k) g_v[k-b],
     //                     M_v(k) = sum over the rows of v at step k of 4 dd_r dbar_r dbar_r'   (2x2, aggregated)
     //   omega row         S[n][(v,a)] = -(A'dd)[(v,a)],  S[n][n] = sum dd + dg[n]
     //   pair blocks (j>i) S[(j,b),(i,a)] = -sum_{k>=max(a,b)} aj[k][b] ai[k][a],  ai = 2 dd_r dbar_r.g_i[k-a],
-    //                     aj = 2 dbar_r.g_j[k-b]: one warp per block, factors staged in its scratch slot.
+    //                     aj = 2 dbar_r.g_j[k-b]: one warp per block on the tensor path (pair_block_mma).
     template <class Mem>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg)
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg SCP_TIMER_ARG)
     {
         double *S = m.S;
         const double sd = forces(cta, dd);            // frc = A'dd in force form (for the omega row)
+        SCP_TIMER(12)
         CTA_PHASE(tid)
             for (int c = tid; c < n; c += cta.nt) {   // M_v(k)
                 const int v = c / Hp, k = c - v * Hp;
@@ -168,6 +234,7 @@ struct PairOp {
                 S[scp_sidx(c, c)] = 1.0;
             }
         CTA_PHASE_END
+        SCP_TIMER(13)
         CTA_PHASE(tid)
             // omega row
             for (int c = tid; c < n; c += cta.nt) {
@@ -195,7 +262,7 @@ struct PairOp {
                 }
                 S[scp_sidx(v * Hp + a, v * Hp + b)] = acc;
             }
-            // pair blocks without scratch: entry by entry (large horizons)
+            // pair blocks entry by entry (horizons beyond the accumulator budget of pair_block_mma)
             if (alpha_slots == 0) {
                 const int npair = nVeh * (nVeh - 1) >> 1;
                 for (int e = tid; e < npair * Hp * Hp; e += cta.nt) {
@@ -211,46 +278,17 @@ struct PairOp {
                 }
             }
         CTA_PHASE_END
+        SCP_TIMER(14)
         if (alpha_slots > 0) {
             const int npair = nVeh * (nVeh - 1) >> 1;
-            const int tri = Hp * (Hp + 1) >> 1, hh = (Hp + 1) >> 1;
             WARP_SECTION(w, nw)
-                const int nslot = alpha_slots < nw ? alpha_slots : nw;
-                if (w < nslot) {
-                    double *ai = alpha + (size_t)w * alpha_stride, *aj = ai + tri;
-                    for (int p = w; p < npair; p += nslot) {
+                WARP_PHASE(lane)
+                    for (int p = w; p < npair; p += nw) {
                         int i = 0, q = p;
                         while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
-                        const int j = i + 1 + q, r0 = p * Hp;
-                        const double *gi = g + (size_t)i * Hp * 2, *gj = g + (size_t)j * Hp * 2;
-                        WARP_PHASE(lane)
-                            for (int t = lane; t < tri; t += 32) {
-                                int k, a;
-                                scp_tri_decode(t, &k, &a);
-                                const int r = r0 + k;
-                                ai[t] = dd[r] * coef2(gi, r, k - a);
-                                aj[t] = coef2(gj, r, k - a);
-                            }
-                        WARP_PHASE_END
-                        WARP_PHASE(lane)
-                            for (int t = lane; t < hh * hh; t += 32) {          // 2x2 patches of the Hp x Hp block
-                                const int b0 = (t / hh) * 2, a0 = (t - (t / hh) * hh) * 2;
-                                const bool b1ok = b0 + 1 < Hp, a1ok = a0 + 1 < Hp;
-                                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-                                for (int k = (a0 > b0 ? a0 : b0); k < Hp; ++k) {
-                                    const int kb = k * (k + 1) >> 1;
-                                    const double x0 = ai[kb + a0], x1 = (a1ok && a0 + 1 <= k) ? ai[kb + a0 + 1] : 0.0;
-                                    const double y0 = aj[kb + b0], y1 = (b1ok && b0 + 1 <= k) ? aj[kb + b0 + 1] : 0.0;
-                                    c00 += y0 * x0; c01 += y0 * x1; c10 += y1 * x0; c11 += y1 * x1;
-                                }
-                                S[scp_sidx(j * Hp + b0, i * Hp + a0)] = -c00;
-                                if (a1ok) S[scp_sidx(j * Hp + b0, i * Hp + a0 + 1)] = -c01;
-                                if (b1ok) S[scp_sidx(j * Hp + b0 + 1, i * Hp + a0)] = -c10;
-                                if (a1ok && b1ok) S[scp_sidx(j * Hp + b0 + 1, i * Hp + a0 + 1)] = -c11;
-                            }
-                        WARP_PHASE_END
+                        pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
                     }
-                }
+                WARP_PHASE_END
             WARP_SECTION_END
             CTA_SYNC
         }

@@ -581,12 +581,12 @@ SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 
 struct ScpMem {
     IpmMem ipm;
-    double *g, *dbar, *resp, *frc, *ucur, *Msm, *alpha, *Hs;
-    int alpha_slots, alpha_stride;
+    double *g, *dbar, *resp, *frc, *ucur, *Msm, *Hs;
+    int alpha_slots;
     bool H_local;      // Hs is shared-resident: the instance's cost blocks are copied there once per instance
 };
 
-// alpha_slots: number of per-warp scratch slots for the pair-block products of the normal matrix (0 = none)
+// alpha_slots: pair-block mode of the normal matrix (> 0: tensor path, 0: entry by entry; see PairOp)
 // want_H: keep a shared-memory copy of the instance's cost blocks (read every iteration); otherwise they are read
 // from global memory.
 SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int alpha_slots, int want_H)
@@ -600,8 +600,6 @@ SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int
     s.ucur = bp.take(s.ipm.n1p);
     s.Msm = bp.take((size_t)n * 3);
     s.alpha_slots = alpha_slots;
-    s.alpha_stride = Hp * (Hp + 1);
-    s.alpha = bp.take((size_t)alpha_slots * s.alpha_stride);
     s.Hs = want_H ? bp.take((size_t)n * Hp) : 0;
     s.H_local = want_H && bp.last_shared;
     ipm_carve_big(bp, s.ipm);
@@ -672,7 +670,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
     op.g = s.g; op.H = s.H_local ? s.Hs : HB; op.dbar = s.dbar; op.resp = s.resp; op.frc = s.frc; op.red = m.red;
     op.xom = 0.0; op.wsum = 0.0;
-    op.Msm = s.Msm; op.alpha = s.alpha; op.alpha_slots = s.alpha_slots; op.alpha_stride = s.alpha_stride;
+    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots;
 
     double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
     const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance

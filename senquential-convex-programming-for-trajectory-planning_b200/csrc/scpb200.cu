@@ -408,19 +408,10 @@ static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
 {
     pl->threads = env_int("SCPB200_THREADS", 256);
     const int nVeh = d->nVeh, Hp = d->Hp, nObst = d->nObst;
-    // per-warp scratch slots for the pair-block products: one per warp if that keeps the occupancy target,
-    // else fewer
-    int slots = pl->threads / 32;
+    // pair blocks of the normal matrix on the tensor path while the horizon fits its accumulators
+    int slots = Hp <= 8 * SCP_PAIR_NA ? 1 : 0;
     const int want = env_int("SCPB200_ALPHA_SLOTS", -1);
-    if (want >= 0 && want < slots) slots = want;
-    const size_t target = ((size_t)SCP_SM_SHARED_BYTES / SCP_MIN_CTAS - 1024) / 8;
-    while (slots > 1) {
-        size_t shu, glu;
-        scp_footprint(nVeh, Hp, nObst, slots, 1, (size_t)1 << 40, &shu, &glu);
-        if (shu <= target) break;
-        slots /= 2;
-    }
-    if (Hp > 24) slots = 0;                                    // long horizons: entry-by-entry pair blocks
+    if (want == 0) slots = 0;
     pl->alpha_slots = slots;
     // first with the cost blocks shared-resident, then without
     for (int want_H = 1; want_H >= 0; --want_H) {

@@ -54,9 +54,10 @@ if os.environ.get("SCPB200_LIB", "").endswith("timers.so"):
     lib = capi.load()
     lib.scpb200_debug_read_timers(arr)
     names = {0: "misc/outside", 1: "form_normal", 2: "chol potrf", 3: "chol trsm", 4: "chol gemm", 5: "diag inverses", 6: "inv W", 7: "inv product",
-             8: "solve", 9: "residual phase", 10: "pass rhs (w1, A'w1)", 11: "pass dz/ds/step"}
+             8: "solve", 9: "residual phase", 10: "pass rhs (w1, A'w1)", 11: "pass dz/ds/step",
+             12: "form: forces", 13: "form: M_v(k)", 14: "form: omega+diag"}
     tot = sum(arr)
     nfac = int(bs.ipm_iters.sum()) + int(bs.scp_iters.sum())
     print(f"phase timers, all steps (cycles of thread 0 summed over CTAs); factorisations in the last step: {nfac}")
-    for i in range(12):
+    for i in range(15):
         print(f"  {names[i]:24s} {100.0 * arr[i] / tot:5.1f}%   {arr[i] / 1e6:10.2f} Mcyc   {arr[i] / max(1, nfac):10.0f} cyc/factorisation")
