@@ -68,13 +68,18 @@ typedef struct scpb200_params {
     double qp_dual_reg;      /* proximal regularisation of s/z in the normal matrix (default 1e-12) */
     double inf_bound;        /* |bound| >= inf_bound means "no bound" (default 1e20, Gurobi's convention) */
     int32_t ipm_max_iter;    /* default 60 */
-    int32_t reserved0;
+    int32_t qp_warm_start;   /* scpb200_scp_solve only: start the QP of SCP iteration k+1 from an interior iterate of QP k
+                              * (same unique minimiser, fewer interior-point iterations); 0 = every QP from the coneqp
+                              * starting point.  Default 1. */
     /* extensions, default = reference behaviour */
     double trust_radius;     /* |u - ubar|_inf <= rho folded into lb/ub; +inf (>= 1e300) = off */
     double noise_sigma;      /* std-dev of the process noise added to f(x,u)[0:2] (Model.py:84-86: 3e-6); 0 = off */
     uint64_t seed;           /* Philox4x32-10 key */
     uint32_t instance0;      /* global index of instance 0 of this call (sharding keeps streams G-independent) */
     uint32_t noise_counter;  /* draw counter (e.g. the MPC step index) */
+    double qp_warm_relgap;   /* the iterate kept for the next QP is the first with relative gap <= this (default 1.0: an early, well-centred iterate; measured best on the 1024-instance benchmark) */
+    int32_t qp_warm_max_iter; /* a warm-started QP not converged after this many iterations restarts cold (default 30) */
+    int32_t reserved1;
 } scpb200_params;
 
 /* width of one row of the per-iteration log of scpb200_scp_solve (SCP_controller.py:169-189, scalar fields) */

@@ -33,6 +33,14 @@
 struct IpmCtl {
     double abstol, reltol, feastol, dual_reg, inf_bound;
     int max_iter;
+    // Warm start across the QPs of one SCP loop (consecutive QPs differ only in the linearisation point):
+    //   snap      global memory for one interior iterate (x, s, z of every row; ipm_snap_doubles()), or null
+    //   warm      start from the iterate in `snap` instead of the coneqp starting point
+    //   snap_relgap  the iterate saved is the first one with relative gap <= snap_relgap: centred, still far enough
+    //             from the boundary for the next QP's active set to change (a converged iterate would jam)
+    double *snap;
+    double snap_relgap;
+    int warm;
 };
 
 // Pointers into the CTA's working set.  n1p = n1 rounded up to the tile size; vectors of length n1p have
@@ -54,7 +62,34 @@ struct IpmMem {
 struct IpmResult {
     double fval, gap, relgap, pres, dres;
     int iters, status;
+    int snap_saved;      // an iterate was written to ctl.snap during this solve
 };
+
+SCP_HDFN size_t ipm_snap_doubles(int n1p, int mc) { return (size_t)5 * n1p + 2 * (size_t)((mc + 1) & ~1); }
+
+// Copy the interior iterate (x, sA, zA, sU, zU, sL, zL) to / from the snapshot area (one phase).
+SCP_FN void ipm_snapshot(Cta &cta, const IpmMem &m, double *snap, bool save)
+{
+    const int n1p = m.n1p, mc = m.mc;
+    const size_t rows = (size_t)((mc + 1) & ~1);
+    double *px = snap, *psA = px + n1p, *pzA = psA + rows, *psU = pzA + rows, *pzU = psU + n1p, *psL = pzU + n1p,
+           *pzL = psL + n1p;
+    CTA_PHASE(tid)
+        if (save) {
+            for (int c = tid; c < n1p; c += cta.nt) {
+                px[c] = m.x[c]; psU[c] = m.sU[c]; pzU[c] = m.zU[c]; psL[c] = m.sL[c]; pzL[c] = m.zL[c];
+            }
+            for (int r = tid; r < mc; r += cta.nt) { psA[r] = m.sA[r]; pzA[r] = m.zA[r]; }
+        } else {
+            for (int c = tid; c < n1p; c += cta.nt) {
+                m.x[c] = SCP_LD_COHERENT(px + c);
+                m.sU[c] = SCP_LD_COHERENT(psU + c); m.zU[c] = SCP_LD_COHERENT(pzU + c);
+                m.sL[c] = SCP_LD_COHERENT(psL + c); m.zL[c] = SCP_LD_COHERENT(pzL + c);
+            }
+            for (int r = tid; r < mc; r += cta.nt) { m.sA[r] = SCP_LD_COHERENT(psA + r); m.zA[r] = SCP_LD_COHERENT(pzA + r); }
+        }
+    CTA_PHASE_END
+}
 
 // ------------------------------------------------------------------------------------------------ 8x8 tile leaves
 // All 8x8 tiles (normal matrix, scratch) use the half-row-swapped layout of scp_tphys().
@@ -406,71 +441,75 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
     const double resx0 = fmax(1.0, sqrt(cta_red_sum(cta, red, 1)));
     const double resz0 = fmax(1.0, sqrt(cta_red_sum(cta, red, 2)));
 
-    // ---- starting point (coneqp): (P + G'G) x = G'h - q ; z = Gx - h ; s = -z ; shift ------------
-    CTA_PHASE(tid)
-        for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = 1.0;            // dd = 1
-        for (int c = tid; c < n1p; c += cta.nt) {
-            double d = 0.0;
-            if (ipm_has_ub(m, ctl, c)) d += 1.0;
-            if (ipm_has_lb(m, ctl, c)) d += 1.0;
-            m.tn[c] = d;                                                   // box part of the diagonal
+    if (ctl.warm) {
+        ipm_snapshot(cta, m, ctl.snap, false);
+    } else {
+        // ---- starting point (coneqp): (P + G'G) x = G'h - q ; z = Gx - h ; s = -z ; shift ------------
+        CTA_PHASE(tid)
+            for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = 1.0;            // dd = 1
+            for (int c = tid; c < n1p; c += cta.nt) {
+                double d = 0.0;
+                if (ipm_has_ub(m, ctl, c)) d += 1.0;
+                if (ipm_has_lb(m, ctl, c)) d += 1.0;
+                m.tn[c] = d;                                                   // box part of the diagonal
+            }
+        CTA_PHASE_END
+        SCP_TIMER(0)
+        op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
+        op.prep(cta, (const double *)0, m.bA);
+        CTA_PHASE(tid)
+            for (int c = tid; c < n1; c += cta.nt) {
+                double rhs = op.col_dot(c) - m.q[c];
+                if (ipm_has_ub(m, ctl, c)) rhs += m.ub[c];
+                if (ipm_has_lb(m, ctl, c)) rhs += m.lb[c];
+                m.x[c] = rhs;
+            }
+        CTA_PHASE_END
+        SCP_TIMER(1)
+        chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
+        chol_solve_tiles(cta, m, m.x, m.tn);
+        SCP_TIMER(8)
+        op.prep(cta, m.x, (const double *)0);
+        CTA_RED_BEGIN(cta, 3)
+        CTA_PHASE(tid)
+            double nrm = 0.0, ts = -1e300, tz = -1e300;
+            for (int r = tid; r < mc; r += cta.nt) {
+                const double z = op.row_dot(r) - m.bA[r];
+                m.zA[r] = z; m.sA[r] = -z;
+                nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
+            }
+            for (int c = tid; c < n1p; c += cta.nt) {
+                if (ipm_has_ub(m, ctl, c)) {
+                    const double z = m.x[c] - m.ub[c];
+                    m.zU[c] = z; m.sU[c] = -z; nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
+                } else { m.zU[c] = 0.0; m.sU[c] = 1.0; }
+                if (ipm_has_lb(m, ctl, c)) {
+                    const double z = m.lb[c] - m.x[c];
+                    m.zL[c] = z; m.sL[c] = -z; nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
+                } else { m.zL[c] = 0.0; m.sL[c] = 1.0; }
+            }
+            CTA_RED_SUM(cta, red, 0, tid, nrm)
+            CTA_RED_MAX(cta, red, 1, tid, ts)
+            CTA_RED_MAX(cta, red, 2, tid, tz)
+        CTA_PHASE_END_RED(cta, red, 3)
+        double as_shift, az_shift;
+        {
+            const double nrm = sqrt(cta_red_sum(cta, red, 0));
+            const double ts = cta_red_max(cta, red, 1), tz = cta_red_max(cta, red, 2);
+            const double thr = -1e-8 * fmax(nrm, 1.0);
+            as_shift = (ts >= thr) ? 1.0 + ts : 0.0;
+            az_shift = (tz >= thr) ? 1.0 + tz : 0.0;
         }
-    CTA_PHASE_END
-    SCP_TIMER(0)
-    op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
-    op.prep(cta, (const double *)0, m.bA);
-    CTA_PHASE(tid)
-        for (int c = tid; c < n1; c += cta.nt) {
-            double rhs = op.col_dot(c) - m.q[c];
-            if (ipm_has_ub(m, ctl, c)) rhs += m.ub[c];
-            if (ipm_has_lb(m, ctl, c)) rhs += m.lb[c];
-            m.x[c] = rhs;
-        }
-    CTA_PHASE_END
-    SCP_TIMER(1)
-    chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
-    chol_solve_tiles(cta, m, m.x, m.tn);
-    SCP_TIMER(8)
-    op.prep(cta, m.x, (const double *)0);
-    CTA_RED_BEGIN(cta, 3)
-    CTA_PHASE(tid)
-        double nrm = 0.0, ts = -1e300, tz = -1e300;
-        for (int r = tid; r < mc; r += cta.nt) {
-            const double z = op.row_dot(r) - m.bA[r];
-            m.zA[r] = z; m.sA[r] = -z;
-            nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
-        }
-        for (int c = tid; c < n1p; c += cta.nt) {
-            if (ipm_has_ub(m, ctl, c)) {
-                const double z = m.x[c] - m.ub[c];
-                m.zU[c] = z; m.sU[c] = -z; nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
-            } else { m.zU[c] = 0.0; m.sU[c] = 1.0; }
-            if (ipm_has_lb(m, ctl, c)) {
-                const double z = m.lb[c] - m.x[c];
-                m.zL[c] = z; m.sL[c] = -z; nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
-            } else { m.zL[c] = 0.0; m.sL[c] = 1.0; }
-        }
-        CTA_RED_SUM(cta, red, 0, tid, nrm)
-        CTA_RED_MAX(cta, red, 1, tid, ts)
-        CTA_RED_MAX(cta, red, 2, tid, tz)
-    CTA_PHASE_END_RED(cta, red, 3)
-    double as_shift, az_shift;
-    {
-        const double nrm = sqrt(cta_red_sum(cta, red, 0));
-        const double ts = cta_red_max(cta, red, 1), tz = cta_red_max(cta, red, 2);
-        const double thr = -1e-8 * fmax(nrm, 1.0);
-        as_shift = (ts >= thr) ? 1.0 + ts : 0.0;
-        az_shift = (tz >= thr) ? 1.0 + tz : 0.0;
+        CTA_PHASE(tid)
+            for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += as_shift; m.zA[r] += az_shift; }
+            for (int c = tid; c < n1p; c += cta.nt) {
+                if (ipm_has_ub(m, ctl, c)) { m.sU[c] += as_shift; m.zU[c] += az_shift; }
+                if (ipm_has_lb(m, ctl, c)) { m.sL[c] += as_shift; m.zL[c] += az_shift; }
+            }
+        CTA_PHASE_END
     }
-    CTA_PHASE(tid)
-        for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += as_shift; m.zA[r] += az_shift; }
-        for (int c = tid; c < n1p; c += cta.nt) {
-            if (ipm_has_ub(m, ctl, c)) { m.sU[c] += as_shift; m.zU[c] += az_shift; }
-            if (ipm_has_lb(m, ctl, c)) { m.sL[c] += as_shift; m.zL[c] += az_shift; }
-        }
-    CTA_PHASE_END
 
-    int iters = 0, status = SCPB200_ST_QP_MAXITER;
+    int iters = 0, status = SCPB200_ST_QP_MAXITER, snap_saved = 0;
     double f0 = 0.0, gap = 0.0, relgap = -1.0, pres = 0.0, dres = 0.0;
     for (iters = 0; iters <= ctl.max_iter; ++iters) {
         // ---- residuals: rx = Px + q + G'z ; rz = s + Gx - h ; costs; e = 1/(s + delta z) -----------
@@ -526,6 +565,10 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         if (pres <= ctl.feastol && dres <= ctl.feastol &&
             (gap <= ctl.abstol || (relgap >= 0.0 && relgap <= ctl.reltol))) { status = 0; break; }
         if (iters == ctl.max_iter) break;
+        if (ctl.snap && !snap_saved && relgap >= 0.0 && relgap <= ctl.snap_relgap) {
+            ipm_snapshot(cta, m, ctl.snap, true);
+            snap_saved = 1;
+        }
         SCP_TIMER(9)
 
         // ---- normal matrix with dd = z e and its inverted factor -----------------------------------
@@ -645,5 +688,5 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
     }
     if (*fixed_p) status |= SCPB200_ST_QP_PIVOT;
     res->fval = f0; res->gap = gap; res->relgap = relgap; res->pres = pres; res->dres = dres;
-    res->iters = iters; res->status = status;
+    res->iters = iters; res->status = status; res->snap_saved = snap_saved;
 }

@@ -160,6 +160,13 @@ __device__ unsigned long long g_scp_prof[32];
 #define SCP_TIMER_PASS
 #endif
 
+// loads of data another CTA may have written during this launch (parked instances) must bypass L1
+#if SCP_DEVICE_BUILD
+#define SCP_LD_COHERENT(ptr) __ldcg(ptr)
+#else
+#define SCP_LD_COHERENT(ptr) (*(ptr))
+#endif
+
 // ------------------------------------------------------------------------------------------------ misc
 SCP_HDFN int scp_imin(int a, int b) { return a < b ? a : b; }
 SCP_HDFN int scp_imax(int a, int b) { return a > b ? a : b; }

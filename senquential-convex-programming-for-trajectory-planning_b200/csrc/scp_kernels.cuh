@@ -570,12 +570,23 @@ SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc)
     m.lb = bp.take(m.n1p); m.sL = bp.take(m.n1p); m.zL = bp.take(m.n1p); m.dsL = bp.take(m.n1p);
     m.dzL = bp.take(m.n1p); m.ccL = bp.take(m.n1p); m.eL = bp.take(m.n1p);
     m.bA = bp.take(mc); m.sA = bp.take(mc); m.zA = bp.take(mc); m.rzA = bp.take(mc);
-    m.dsA = bp.take(mc); m.dzA = bp.take(mc); m.ccA = bp.take(mc); m.eA = bp.take(mc);
+    {
+        const size_t rows = (size_t)((mc + 1) & ~1);          // dsA, dzA, ccA back to back (see ipm_carve_big)
+        double *blk = bp.take(3 * rows);
+        m.dsA = blk; m.dzA = blk ? blk + rows : 0; m.ccA = blk ? blk + 2 * rows : 0;
+    }
+    m.eA = bp.take(mc);
 }
 
 SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 {
-    m.wbuf = bp.take((size_t)(m.T * 64 > 4 * m.n1p ? m.T * 64 : 4 * m.n1p));
+    // The tile scratch of the factor inversion is only live inside chol_tiles, where the row vectors dsA (the scaling
+    // consumed by form_normal), dzA and ccA (written by the passes that follow) are dead: it overlays them when they
+    // are large enough (they are carved back to back).
+    const size_t need = (size_t)(m.T * 64 > 4 * m.n1p ? m.T * 64 : 4 * m.n1p);
+    const size_t rows = (size_t)((m.mc + 1) & ~1);
+    if (3 * rows >= need) m.wbuf = m.dsA;
+    else m.wbuf = bp.take(need);
     m.S = bp.take((size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2);
 }
 
@@ -597,8 +608,11 @@ SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int
     s.dbar = bp.take((size_t)mc * 2);
     s.resp = bp.take((size_t)n * 2);
     s.frc = bp.take((size_t)n * 2);
-    s.ucur = bp.take(s.ipm.n1p);
-    s.Msm = bp.take((size_t)n * 3);
+    // ucur (the SCP iterate) is dead while the interior-point method runs and rx is dead outside it: one array.
+    s.ucur = s.ipm.rx;
+    // Msm (per (vehicle, step) 2x2 aggregates) is only live inside form_normal, where ccA is dead.
+    if ((size_t)n * 3 <= (size_t)mc) s.Msm = s.ipm.ccA;
+    else s.Msm = bp.take((size_t)n * 3);
     s.alpha_slots = alpha_slots;
     s.Hs = want_H ? bp.take((size_t)n * Hp) : 0;
     s.H_local = want_H && bp.last_shared;
@@ -636,15 +650,9 @@ struct ScpIO {
     // by any CTA.  The arithmetic is that of the uninterrupted loop, so results are bit-identical.
     double *state;      // [B][SCP_STATE_W] or null (run to completion)
     int quantum;
+    double *snap;       // [B][ipm_snap_doubles] interior-point warm-start iterates, or null (every QP starts cold)
 };
-#define SCP_STATE_W 6   /* obj0, mv0, it, ipm_total, status bits, pinned (never parked) */
-
-// loads of data another CTA may have written during this launch (parked instances) must bypass L1
-#if SCP_DEVICE_BUILD
-#define SCP_LD_COHERENT(ptr) __ldcg(ptr)
-#else
-#define SCP_LD_COHERENT(ptr) (*(ptr))
-#endif
+#define SCP_STATE_W 8   /* obj0, mv0, it, ipm_total, status bits, pinned (never parked), snapshot valid, (spare) */
 
 // SCP_optimizer (SCP_controller.py:74-197) + the result shaping of SCP_controller (:68-70) for instance b.
 // Returns true when the instance is finished (results written), false when it was parked.
@@ -665,6 +673,10 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     IpmCtl ctl;
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+    ctl.snap = (io.snap && p.qp_warm_start) ? io.snap + (size_t)b * ipm_snap_doubles(m.n1p, mc) : 0;
+    ctl.snap_relgap = p.qp_warm_relgap;
+    ctl.warm = 0;
+    int snap_valid = 0;
 
     PairOp op;
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
@@ -701,6 +713,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     } else {
         obj0 = SCP_LD_COHERENT(stB + 0); mv0 = SCP_LD_COHERENT(stB + 1);
         it = it_resume; ipm_total = (int)SCP_LD_COHERENT(stB + 3); st = (int)SCP_LD_COHERENT(stB + 4);
+        snap_valid = (int)SCP_LD_COHERENT(stB + 6);
         ev.obj = obj0; ev.max_violation = mv0; ev.sum_violations = 0.0; ev.feasible = mv0 > 0.0 ? 0 : 1;
     }
     const int it_park = (stB && stB[5] == 0.0) ? it + (io.quantum > 0 ? io.quantum : 1) : p.max_scp_iter;
@@ -709,7 +722,10 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             // park: u and the loop scalars go back to global memory; another invocation continues from here
             CTA_PHASE(tid)
                 for (int c = tid; c < n; c += cta.nt) uB[c] = s.ucur[c];
-                if (tid == 0) { stB[0] = obj0; stB[1] = mv0; stB[2] = (double)it; stB[3] = (double)ipm_total; stB[4] = (double)st; }
+                if (tid == 0) {
+                    stB[0] = obj0; stB[1] = mv0; stB[2] = (double)it; stB[3] = (double)ipm_total; stB[4] = (double)st;
+                    stB[6] = (double)snap_valid;
+                }
             CTA_PHASE_END
             return false;
         }
@@ -728,7 +744,18 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             }
         CTA_PHASE_END
         IpmResult res;
-        ipm_solve(cta, op, m, ctl, &res);
+        ctl.warm = ctl.snap && snap_valid;
+        if (ctl.warm) {
+            // a warm start that does not converge quickly (the active set moved too far) is abandoned for a cold one
+            const int cap = ctl.max_iter;
+            ctl.max_iter = p.qp_warm_max_iter > 0 ? p.qp_warm_max_iter : cap;
+            ipm_solve(cta, op, m, ctl, &res);
+            ctl.max_iter = cap;
+            if (res.status) { ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
+        } else {
+            ipm_solve(cta, op, m, ctl, &res);
+        }
+        snap_valid = res.snap_saved;
         ipm_total += res.iters;
         if (res.status & SCPB200_ST_QP_MAXITER) st |= SCPB200_ST_QP_MAXITER;
         if (res.status & SCPB200_ST_QP_PIVOT) st |= SCPB200_ST_QP_PIVOT;
@@ -793,6 +820,7 @@ SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc,
     IpmCtl ctl;
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+    ctl.snap = 0; ctl.snap_relgap = 0.0; ctl.warm = 0;
     DenseOp op;
     op.n1 = n1; op.mc = mc;
     op.P = io.P + (size_t)b * n1 * n1;

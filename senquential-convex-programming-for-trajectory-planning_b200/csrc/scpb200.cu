@@ -47,6 +47,9 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->seed = 0;
     p->instance0 = 0;
     p->noise_counter = 0;
+    p->qp_warm_start = 1;
+    p->qp_warm_relgap = 1.0;
+    p->qp_warm_max_iter = 30;
 }
 
 extern "C" int scpb200_device_count(void)
@@ -355,6 +358,14 @@ static size_t queue_bytes(long B)
     const size_t b = queue_cap(B) * sizeof(int) + (size_t)(B < 1 ? 1 : B) * SCP_STATE_W * sizeof(double);
     return (b + 255) & ~(size_t)255;
 }
+// bytes of the interior-point warm-start iterates (one per instance)
+static size_t snap_bytes(const scpb200_dims *d)
+{
+    const int n1p = scp_round_up(d->nVeh * d->Hp + 1, SCP_TILE);
+    const int mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
+    const size_t b = (size_t)(d->B < 1 ? 1 : d->B) * ipm_snap_doubles(n1p, mc) * sizeof(double);
+    return (b + 255) & ~(size_t)255;
+}
 #define SCP_SM_SHARED_BYTES 233472      /* 228 KiB per SM on B200, 1 KiB reserved per resident CTA */
 
 // Pick the occupancy target: the largest number of CTAs per SM (<= max_ctas) for which the whole working set is
@@ -413,13 +424,24 @@ static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
     const int want = env_int("SCPB200_ALPHA_SLOTS", -1);
     if (want == 0) slots = 0;
     pl->alpha_slots = slots;
-    // first with the cost blocks shared-resident, then without
+    // the cost blocks are shared-resident only when that does not cost a resident CTA per SM (otherwise they are
+    // read through L1 from global memory)
+    SolvePlan best;
+    int have = 0;
+    const int force_H = env_int("SCPB200_WANT_H", -1);             // tuning: -1 auto, 0 / 1 forced
     for (int want_H = 1; want_H >= 0; --want_H) {
+        if (force_H >= 0 && want_H != force_H) continue;
         auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu); };
-        int rc = plan_common(k_scp_solve<true>, k_scp_solve<false>, fp, SCP_MIN_CTAS, d->B, pl);
-        pl->want_H = want_H;
-        if (rc || pl->all_shared || want_H == 0) return rc;
+        SolvePlan cand = *pl;
+        int rc = plan_common(k_scp_solve<true>, k_scp_solve<false>, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand);
+        if (rc) return rc;
+        cand.want_H = want_H;
+        if (!have || (cand.all_shared && (!best.all_shared || cand.ctas_per_sm > best.ctas_per_sm))) { best = cand; have = 1; }
     }
+    *pl = best;
+    // plan_common leaves the function attribute of the last candidate: set it for the chosen one
+    if (pl->all_shared) CUDA_TRY(cudaFuncSetAttribute(k_scp_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    else CUDA_TRY(cudaFuncSetAttribute(k_scp_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
     return 0;
 }
 
@@ -446,7 +468,7 @@ extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
     const int n1 = d->nVeh * d->Hp + 1, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
     rc = plan_qp(n1, mc, 1 << 30, &b);
     if (rc) return rc;
-    *bytes = (a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes) + queue_bytes(d->B);
+    *bytes = (a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes) + queue_bytes(d->B) + snap_bytes(d);
     return 0;
 }
 
@@ -651,7 +673,8 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     q.slots = (int *)((char *)ws + WS_HEADER);
     io.state = (double *)((char *)ws + WS_HEADER + (size_t)q.cap * sizeof(int));
     io.quantum = env_int("SCPB200_QUANTUM", 1);
-    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
+    io.snap = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
+    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d));
     k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2), q, io.state);
     CUDA_TRY(cudaGetLastError());
     if (pl.all_shared)

@@ -123,6 +123,9 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
     scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1);
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
+    const size_t snapw = ipm_snap_doubles(s.ipm.n1p, s.ipm.mc);
+    std::vector<double> snapbuf((size_t)d->B * snapw, 0.0);
+    io.snap = snapbuf.data();
     // SCPB200_EMU_QUANTUM=q: exercise the park / resume path of the work-queue scheduler (q SCP iterations per
     // invocation, round-robin over the live instances as the device FIFO does)
     const char *qe = getenv("SCPB200_EMU_QUANTUM");

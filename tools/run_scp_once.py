@@ -26,12 +26,18 @@ ap.add_argument("--max-scp-iter", dest="msi", type=int, default=20)
 ap.add_argument("--step-lo", type=int, default=6)
 ap.add_argument("--step-hi", type=int, default=7)
 ap.add_argument("--assemble", action="store_true")
+ap.add_argument("--warm", type=int, default=-1)
+ap.add_argument("--warm-relgap", dest="wrg", type=float, default=-1.0)
 args = ap.parse_args()
 
 cb = scen.circle_batch(args.batch, Hp=args.hp, step_lo=args.step_lo, step_hi=args.step_hi)
 p = capi.Params()
 capi.load().scpb200_default_params(C.byref(p))
 p.max_scp_iter = args.msi
+if args.warm >= 0:
+    p.qp_warm_start = args.warm
+if args.wrg > 0:
+    p.qp_warm_relgap = args.wrg
 bs = batch.BatchSCP(args.batch, 8, args.hp, params=p)
 bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((args.batch, 8 * args.hp)))
 print("plan", bs.plan())
