@@ -853,112 +853,286 @@ SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc,
 // SCP_controller.py:93-128 to HBM in the reference's layout.  The kernel is a pure streaming write (238 KB per
 // instance at Hp = 10 against 2 KB of input) and 86 % of what it writes is structural zeros (causal rows,
 // block-diagonal P), so it is organised around the store stream:
-//   1. one thread zero-fills the item's P and A row ranges with TMA bulk stores (cp.async.bulk global <- shared)
-//      from a zeroed shared-memory buffer: no per-element instructions, full-width writes;
-//   2. meanwhile the CTA linearises (positions, dbar, right-hand sides) and writes the small vectors;
-//   3. after the bulk group has completed, the ~4 k non-zeros per instance (cost blocks, causal row segments, the
-//      -1 column) are written over the zeros with ordinary stores.
-// Measured alternatives on B200 (246 MB per launch, B = 1024, Hp = 10): per-element 16-byte streaming stores 92 us;
-// staging every 8 KiB chunk (zeros + non-zeros) in shared memory and bulk-storing it 107 us (five CTA barriers
-// per chunk); keeping the next item's zero-fill in flight as well 96 us; this version 64 us; a plain memset of the
-// same bytes 41 us.
-#define SCP_ASM_ZBUF 1024          /* doubles in the zero source buffer (8 KiB) */
-#if SCP_DEVICE_BUILD
-// called by ONE thread: dst[0..nd) = 0 through the async proxy; handles 8-byte-aligned ends with scalar stores
-SCP_FN void scp_bulk_zero(double *dst, size_t nd, const double *zsrc)
-{
-    if (nd && (reinterpret_cast<size_t>(dst) & 15)) { *dst = 0.0; ++dst; --nd; }
-    if (nd & 1) { dst[nd - 1] = 0.0; --nd; }
-    const unsigned src = (unsigned)__cvta_generic_to_shared(zsrc);
-    for (size_t off = 0; off < nd; off += SCP_ASM_ZBUF) {
-        const unsigned bytes = (unsigned)((nd - off < SCP_ASM_ZBUF ? nd - off : SCP_ASM_ZBUF) * 8);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src), "r"(bytes)
-                     : "memory");
-    }
-}
+//   * the item's P and A ranges are cut into 4 KiB chunks of the flat arrays; every warp owns two chunk buffers in
+//     shared memory and works through its chunks alone (no CTA barrier after the linearisation);
+//   * per chunk: zero the buffer (8 STS.128 per lane), write the chunk's few non-zeros (cost blocks, causal row
+//     segments, the -1 column) into it, fence towards the async proxy, and hand the finished 4 KiB to the TMA
+//     (cp.async.bulk global <- shared, SASS UBLKCP); the other buffer is composed while this one drains.
+// Every byte of the output is therefore written exactly once by a full-width bulk store: no second pass over the
+// non-zeros and no sector read-modify-write in L2 (the previous version zero-filled with bulk stores and then
+// scattered 8-byte non-zeros over the zeros: 30.6 MB read back per 246 MB written).
+// Measured on B200 (246 MB per launch, B = 1024, Hp = 10): per-element 16-byte streaming stores 92 us; CTA-wide
+// staging with barriers 107 us; bulk zero-fill + scattered non-zeros 67.5 us; this version: see profiles/; a plain
+// memset of the same bytes 41 us.
+#ifndef SCP_ASM_CHUNK
+#define SCP_ASM_CHUNK 512          /* doubles per chunk buffer (4 KiB) */
+#endif
+#ifndef SCP_ASM_NBUF
+#define SCP_ASM_NBUF 2             /* chunk buffers per warp */
 #endif
 
-// sh: zbuf[SCP_ASM_ZBUF] (zeros, already fenced towards the async proxy), pos[n][2], dbar[mc][2], bA[mc], g[n][2], ubar[n]
-// An instance is split into `nparts` work items over contiguous row ranges of A and P (item 0 also writes the
-// vectors), so that a batch that is not a multiple of the resident CTA count still balances.
-SCP_FN void scp_assemble_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, int part, int nparts,
-                                  const double *g, const double *cterm, const double *H, const double *qv,
-                                  const double *ubar, const double *dsafe, const double *dsafe_obst, const double *obst,
-                                  double *P, double *q, double *A, double *bvec, double *lb, double *ub, double *sh)
+// the chunk [lo, lo + len) of instance-local flat A (row-major [mc][n1]) into buf (already zero).
+// Lane mapping: (row of the chunk = lane >> 2, +8, ...) x (a = lane & 3, +4, ... <= Hp; a == Hp is the -1 column):
+// no divisions in the loops.
+SCP_FN void scp_compose_A(int lane, int nVeh, int Hp, int n1, const int *rowinfo, const double *gs, const double *dbar,
+                          int lo, int len, double *buf)
 {
-    const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp, n1 = n + 1;
-    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
-    ScpBump bp = scp_bump(sh, (size_t)1 << 40, (double *)0, true);
-    double *zbuf = bp.take(SCP_ASM_ZBUF);
-    double *pos = bp.take((size_t)n * 2), *dbar = bp.take((size_t)mc * 2), *bA = bp.take(mc);
-    double *gs = bp.take((size_t)n * 2), *us = bp.take(n);
-    const double *gB = g + (size_t)b * n * 2, *cB = cterm + (size_t)b * n * 2;
-    const double *HB = H + (size_t)b * n * Hp;
-    double *PB = P + (size_t)b * n1 * n1, *AB = A + (size_t)b * mc * n1;
-    const int ar0 = (int)((long)mc * part / nparts), ar1 = (int)((long)mc * (part + 1) / nparts);      // rows of A
-    const int pr0 = (int)((long)n1 * part / nparts), pr1 = (int)((long)n1 * (part + 1) / nparts);      // rows of P
-    CTA_PHASE(tid)
-#if SCP_DEVICE_BUILD
-        if (tid == 0) {
-            scp_bulk_zero(PB + (size_t)pr0 * n1, (size_t)(pr1 - pr0) * n1, zbuf);
-            scp_bulk_zero(AB + (size_t)ar0 * n1, (size_t)(ar1 - ar0) * n1, zbuf);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-#else
-        (void)zbuf;
-        for (size_t e = (size_t)pr0 * n1 + tid; e < (size_t)pr1 * n1; e += cta.nt) PB[e] = 0.0;
-        for (size_t e = (size_t)ar0 * n1 + tid; e < (size_t)ar1 * n1; e += cta.nt) AB[e] = 0.0;
-#endif
-        for (int e = tid; e < n * 2; e += cta.nt) gs[e] = gB[e];
-        for (int c = tid; c < n; c += cta.nt) us[c] = ubar[(size_t)b * n + c];
-    CTA_PHASE_END
-    scp_linearise(cta, nVeh, Hp, nObst, gs, cB, us, dsafe + (size_t)b * nVeh * nVeh,
-                  nObst ? dsafe_obst + (size_t)b * nVeh * nObst : 0, nObst ? obst + (size_t)b * nObst * Hp * 2 : 0,
-                  p.dsafeExtra, pos, dbar, bA);
-    CTA_PHASE(tid)
-        // q, lb, ub, b
-        double *qB = q + (size_t)b * n1, *lbB = lb + (size_t)b * n1, *ubB = ub + (size_t)b * n1;
-        for (int c = tid; c < (part == 0 ? n1 : 0); c += cta.nt) {
-            double lo = -p.uLim, hi = p.uLim;
-            if (c < n) {
-                if (p.trust_radius < 1e300) { lo = fmax(lo, us[c] - p.trust_radius); hi = fmin(hi, us[c] + p.trust_radius); }
-                qB[c] = qv[(size_t)b * n + c];
-            } else { lo = 0.0; hi = p.omega_ub; qB[c] = p.omega_weight; }
-            lbB[c] = lo;
-            ubB[c] = hi;
-        }
-        for (int r = ar0 + tid; r < ar1; r += cta.nt) bvec[(size_t)b * mc + r] = bA[r];
-#if SCP_DEVICE_BUILD
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // zero-fill complete ...
-            asm volatile("fence.proxy.async;" ::: "memory");                // ... and ordered before the generic-proxy stores below
-        }
-#endif
-    CTA_PHASE_END
-    CTA_PHASE(tid)
-        // P = blkdiag(2 H, 0): the cost blocks over the zeros (SCP_controller.py:120,124)
-        for (int e = pr0 * Hp + tid; e < (pr1 < n ? pr1 : n) * Hp; e += cta.nt) {
-            const int row = e / Hp, bb = e - row * Hp, v = row / Hp;
-            PB[(size_t)row * n1 + v * Hp + bb] = 2.0 * HB[e];
-        }
-        // A: causal segments of the two vehicle blocks and the -1 of the slack column (SCP_controller.py:97-128)
-        for (int t = ar0 * Hp + tid; t < ar1 * Hp; t += cta.nt) {
-            const int row = t / Hp, a = t - row * Hp;
-            int i, j, o, kk;
-            scp_row_decode(nVeh, Hp, nObst, mcv, row, &i, &j, &o, &kk);
-            double *Ar = AB + (size_t)row * n1;
-            if (a == 0) Ar[n] = -1.0;                                                      // SCP_controller.py:125
-            if (a <= kk) {
-                const double dx = dbar[row * 2], dy = dbar[row * 2 + 1];
+    (void)nVeh;
+    const int n = n1 - 1;
+    const int r0 = lo / n1, r1 = (lo + len - 1) / n1;
+    for (int row = r0 + (lane >> 2); row <= r1; row += 8) {
+        const int info = rowinfo[row], i = info & 0xff, j = (info >> 8) & 0xff, kk = info >> 16;   // j = 0xff: obstacle row
+        const int base = row * n1 - lo;
+        const double dx = dbar[row * 2], dy = dbar[row * 2 + 1];
+        for (int a = lane & 3; a <= Hp; a += 4) {
+            if (a == Hp) {                                                                         // SCP_controller.py:125
+                const int idx = base + n;
+                if (idx >= 0 && idx < len) buf[idx] = -1.0;
+            } else if (a <= kk) {
                 double vi = -2.0 * (dx * gs[(i * Hp + kk - a) * 2] + dy * gs[(i * Hp + kk - a) * 2 + 1]);
-                if (fabs(vi) <= 1e-20) vi = 0.0;                                           // SCP_controller.py:128
-                Ar[i * Hp + a] = vi;
-                if (o < 0) {
+                if (fabs(vi) <= 1e-20) vi = 0.0;                                                   // SCP_controller.py:128
+                const int ii = base + i * Hp + a;
+                if (ii >= 0 && ii < len) buf[ii] = vi;
+                if (j != 0xff) {
                     double vj = 2.0 * (dx * gs[(j * Hp + kk - a) * 2] + dy * gs[(j * Hp + kk - a) * 2 + 1]);
                     if (fabs(vj) <= 1e-20) vj = 0.0;
-                    Ar[j * Hp + a] = vj;
+                    const int jj = base + j * Hp + a;
+                    if (jj >= 0 && jj < len) buf[jj] = vj;
                 }
             }
         }
+    }
+}
+
+// the chunk [lo, lo + len) of instance-local flat P = blkdiag(2 H, 0) (row-major [n1][n1]) into buf (already zero)
+SCP_FN void scp_compose_P(int lane, int Hp, int n1, const double *HB, int lo, int len, double *buf)
+{
+    const int n = n1 - 1;
+    const int r0 = lo / n1;
+    int r1 = (lo + len - 1) / n1;
+    if (r1 >= n) r1 = n - 1;                                  // the omega row is zero (SCP_controller.py:124)
+    for (int row = r0 + (lane >> 2); row <= r1; row += 8) {
+        const int v = row / Hp, base = row * n1 - lo + v * Hp;
+        for (int bb = lane & 3; bb < Hp; bb += 4) {
+            const int idx = base + bb;
+            if (idx >= 0 && idx < len) buf[idx] = 2.0 * HB[(size_t)row * Hp + bb];                // SCP_controller.py:120
+        }
+    }
+}
+
+// rowinfo[r] = i | j << 8 | k << 16 (j = 0xff for obstacle rows); built once per kernel, dims only
+SCP_FN void scp_asm_rowinfo(Cta &cta, int nVeh, int Hp, int nObst, int *rowinfo)
+{
+    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    CTA_PHASE(tid)
+        for (int r = tid; r < mc; r += cta.nt) {
+            int i, j, o, k;
+            scp_row_decode(nVeh, Hp, nObst, mcv, r, &i, &j, &o, &k);
+            rowinfo[r] = i | ((o < 0 ? j : 0xff) << 8) | (k << 16);
+        }
     CTA_PHASE_END
+}
+
+struct ScpAsmMem {
+    double *pos, *dbar, *gs, *us, *cs, *ds, *dso, *obs, *bufs;      // staged inputs: g, ubar, cterm, dsafe, (dsafe_obst, obst)
+    int *rowinfo;
+    int nstage;             // doubles of the staged-input block gs .. obs (contiguous)
+};
+// doubles of shared memory for nw warps
+SCP_HDFN size_t scp_asm_carve(ScpAsmMem &a, double *sh, int nVeh, int Hp, int nObst, int nw)
+{
+    const int n = nVeh * Hp, mc = Hp * (nVeh * (nVeh - 1) / 2 + nVeh * nObst);
+    ScpBump bp = scp_bump(sh, (size_t)1 << 40, (double *)0, true);
+    a.bufs = bp.take((size_t)nw * SCP_ASM_NBUF * SCP_ASM_CHUNK);          // first: 16-byte (in fact 128-byte) aligned
+    a.pos = bp.take((size_t)n * 2); a.dbar = bp.take((size_t)mc * 2);
+    // one contiguous block, every piece an even number of doubles (take() rounds up)
+    const size_t s0 = bp.sh_off;
+    a.gs = bp.take((size_t)n * 2); a.us = bp.take(n); a.cs = bp.take((size_t)n * 2); a.ds = bp.take((size_t)nVeh * nVeh);
+    a.dso = bp.take((size_t)nVeh * nObst); a.obs = bp.take((size_t)nObst * Hp * 2);
+    a.nstage = (int)(bp.sh_off - s0);
+    a.rowinfo = (int *)bp.take((size_t)(mc + 1) / 2);
+    return bp.sh_off;
+}
+
+// element e of the staged-input block of instance b, read from global memory
+SCP_FN double scp_asm_stage_src(const scpb200_dims &d, int b, int e, const double *g, const double *cterm,
+                                const double *ubar, const double *dsafe, const double *dsafe_obst, const double *obst)
+{
+    const int n = d.nVeh * d.Hp;
+    int o = 0, len;
+    len = n * 2;            if (e < o + ((len + 1) & ~1)) return e - o < len ? g[(size_t)b * len + (e - o)] : 0.0;       o += (len + 1) & ~1;
+    len = n;                if (e < o + ((len + 1) & ~1)) return e - o < len ? ubar[(size_t)b * len + (e - o)] : 0.0;    o += (len + 1) & ~1;
+    len = n * 2;            if (e < o + ((len + 1) & ~1)) return e - o < len ? cterm[(size_t)b * len + (e - o)] : 0.0;   o += (len + 1) & ~1;
+    len = d.nVeh * d.nVeh;  if (e < o + ((len + 1) & ~1)) return e - o < len ? dsafe[(size_t)b * len + (e - o)] : 0.0;   o += (len + 1) & ~1;
+    len = d.nVeh * d.nObst; if (e < o + ((len + 1) & ~1)) return e - o < len ? dsafe_obst[(size_t)b * len + (e - o)] : 0.0; o += (len + 1) & ~1;
+    len = d.nObst * d.Hp * 2;
+    return e - o < len ? obst[(size_t)b * len + (e - o)] : 0.0;
+}
+
+#define SCP_ASM_PF 4        /* staged-input doubles a thread can hold in registers across the store phase */
+
+// Work items first, first + stride, ... < nitems, item = (instance, part): an instance is split into `nparts` items
+// over contiguous row ranges of A and P (part 0 also writes q, lb, ub), so that a batch that is not a multiple of the
+// resident CTA count still balances.  Per item:
+//   phase 1  predicted positions at ubar from the staged inputs            (forward_U, SCP_controller.py:199-213)
+//   phase 2  linearisation rows dbar, b (SCP_controller.py:97-114) and the small vectors q, lb, ub, b -> HBM;
+//            then every thread fetches its share of the NEXT item's inputs into registers (the loads are in flight
+//            while the warps stream this item's chunks, so no item waits on global-memory latency)
+//   chunks   per warp, no CTA barrier (see above)
+//   phase 3  the prefetched inputs -> the staged block
+SCP_FN void scp_assemble_items(Cta &cta, const scpb200_dims &d, const scpb200_params &p, long first, long stride, long nitems,
+                               int nparts, const double *g, const double *cterm, const double *H, const double *qv,
+                               const double *ubar, const double *dsafe, const double *dsafe_obst, const double *obst,
+                               double *P, double *q, double *A, double *bvec, double *lb, double *ub, const ScpAsmMem &sm)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp, n1 = n + 1;
+    const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
+    double *pos = sm.pos, *dbar = sm.dbar, *gs = sm.gs, *us = sm.us;
+    const long NP = (long)n1 * n1, NA = (long)mc * n1;
+#if SCP_DEVICE_BUILD
+    const bool prefetch = sm.nstage <= SCP_ASM_PF * cta.nt;
+    double pf[SCP_ASM_PF];
+    unsigned gen = 0;
+#else
+    const bool prefetch = false;
+    unsigned gen = 0;
+#endif
+    if (first < nitems) {
+        CTA_PHASE(tid)
+            for (int e = tid; e < sm.nstage; e += cta.nt)
+                gs[e] = scp_asm_stage_src(d, (int)(first / nparts), e, g, cterm, ubar, dsafe, dsafe_obst, obst);
+        CTA_PHASE_END
+    }
+    for (long item = first; item < nitems; item += stride) {
+        const int b = (int)(item / nparts), part = (int)(item - (long)b * nparts);
+        const long nxt = item + stride;
+        const int bn = nxt < nitems ? (int)(nxt / nparts) : -1;           // instance of the next item (-1: none)
+        const double *HB = H + (size_t)b * n * Hp;
+        const int ar0 = (int)((long)mc * part / nparts), ar1 = (int)((long)mc * (part + 1) / nparts);      // rows of A
+        const int pr0 = (int)((long)n1 * part / nparts), pr1 = (int)((long)n1 * (part + 1) / nparts);      // rows of P
+        scp_positions(cta, nVeh, Hp, gs, sm.cs, us, pos);
+        CTA_PHASE(tid)
+            for (int r = tid; r < mc; r += cta.nt) {
+                const int info = sm.rowinfo[r], i = info & 0xff, j = (info >> 8) & 0xff, k = info >> 16;
+                double dx, dy, bx, by, sbar;
+                if (j != 0xff) {
+                    dx = pos[(i * Hp + k) * 2] - pos[(j * Hp + k) * 2];
+                    dy = pos[(i * Hp + k) * 2 + 1] - pos[(j * Hp + k) * 2 + 1];
+                    bx = sm.cs[(i * Hp + k) * 2] - sm.cs[(j * Hp + k) * 2];
+                    by = sm.cs[(i * Hp + k) * 2 + 1] - sm.cs[(j * Hp + k) * 2 + 1];
+                    sbar = sm.ds[i * nVeh + j] + p.dsafeExtra;
+                } else {
+                    const int o = ((r - mcv) / Hp) % nObst;
+                    const double ox = sm.obs[(o * Hp + k) * 2], oy = sm.obs[(o * Hp + k) * 2 + 1];
+                    dx = pos[(i * Hp + k) * 2] - ox;
+                    dy = pos[(i * Hp + k) * 2 + 1] - oy;
+                    bx = sm.cs[(i * Hp + k) * 2] - ox;
+                    by = sm.cs[(i * Hp + k) * 2 + 1] - oy;
+                    sbar = sm.dso[i * nObst + o] + p.dsafeExtra;
+                }
+                dbar[r * 2] = dx;
+                dbar[r * 2 + 1] = dy;
+                if (r >= ar0 && r < ar1)
+                    bvec[(size_t)b * mc + r] = -sbar * sbar - (dx * dx + dy * dy) + 2.0 * (dx * bx + dy * by);
+            }
+            if (part == 0) {
+                double *qB = q + (size_t)b * n1, *lbB = lb + (size_t)b * n1, *ubB = ub + (size_t)b * n1;
+                for (int c = tid; c < n1; c += cta.nt) {
+                    double lo = -p.uLim, hi = p.uLim;
+                    if (c < n) {
+                        if (p.trust_radius < 1e300) { lo = fmax(lo, us[c] - p.trust_radius); hi = fmin(hi, us[c] + p.trust_radius); }
+                        qB[c] = qv[(size_t)b * n + c];
+                    } else { lo = 0.0; hi = p.omega_ub; qB[c] = p.omega_weight; }
+                    lbB[c] = lo;
+                    ubB[c] = hi;
+                }
+            }
+#if SCP_DEVICE_BUILD
+            if (prefetch && bn >= 0 && bn != b) {
+#pragma unroll
+                for (int s = 0; s < SCP_ASM_PF; ++s) {
+                    const int e = tid + s * cta.nt;
+                    pf[s] = e < sm.nstage ? scp_asm_stage_src(d, bn, e, g, cterm, ubar, dsafe, dsafe_obst, obst) : 0.0;
+                }
+            }
+#endif
+        CTA_PHASE_END
+        // the two flat ranges of this item, in elements of the whole P / A arrays (16-byte alignment is a property of
+        // the global element index: odd leading / trailing elements go out as plain stores)
+        const long lo0 = (long)b * NP + (long)pr0 * n1, hi0 = (long)b * NP + (long)pr1 * n1;
+        const long lo1 = (long)b * NA + (long)ar0 * n1, hi1 = (long)b * NA + (long)ar1 * n1;
+        const int h0 = (int)(lo0 & 1), h1 = (int)(lo1 & 1);
+        const int nc0 = hi0 > lo0 ? h0 + (int)((hi0 - lo0 - h0 + SCP_ASM_CHUNK - 1) / SCP_ASM_CHUNK) : 0;
+        const int nc1 = hi1 > lo1 ? h1 + (int)((hi1 - lo1 - h1 + SCP_ASM_CHUNK - 1) / SCP_ASM_CHUNK) : 0;
+        WARP_SECTION(w, nw)
+            for (int t = w; t < nc0 + nc1; t += nw) {
+                const bool isA = t >= nc0;
+                const int tt = isA ? t - nc0 : t, h = isA ? h1 : h0;
+                const long lo = isA ? lo1 : lo0, hi = isA ? hi1 : hi0;
+                long c0;
+                int len;
+                if (h && tt == 0) { c0 = lo; len = 1; }
+                else {
+                    c0 = lo + h + (long)(tt - h) * SCP_ASM_CHUNK;
+                    len = (int)(hi - c0 < SCP_ASM_CHUNK ? hi - c0 : SCP_ASM_CHUNK);
+                }
+                double *buf = sm.bufs + ((size_t)w * SCP_ASM_NBUF + (gen % SCP_ASM_NBUF)) * SCP_ASM_CHUNK;
+                double *dst = (isA ? A : P) + c0;
+                const int local = (int)(c0 - (long)b * (isA ? NA : NP));
+                WARP_PHASE(lane)
+#if SCP_DEVICE_BUILD
+                    // the bulk store issued from this buffer SCP_ASM_NBUF chunks ago has finished reading it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SCP_ASM_NBUF - 1) : "memory");
+#endif
+                WARP_PHASE_END
+                WARP_PHASE(lane)
+#if SCP_DEVICE_BUILD
+                    double2 *b2 = reinterpret_cast<double2 *>(buf);
+                    for (int e = lane; e < ((len + 1) >> 1); e += 32) b2[e] = make_double2(0.0, 0.0);
+#else
+                    for (int e = lane; e < len; e += 32) buf[e] = 0.0;
+#endif
+                WARP_PHASE_END
+                WARP_PHASE(lane)
+                    if (isA) scp_compose_A(lane, nVeh, Hp, n1, sm.rowinfo, gs, dbar, local, len, buf);
+                    else scp_compose_P(lane, Hp, n1, HB, local, len, buf);
+#if SCP_DEVICE_BUILD
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy
+#endif
+                WARP_PHASE_END
+                WARP_PHASE(lane)
+#if SCP_DEVICE_BUILD
+                    if (lane == 0) {
+                        const int even = len & ~1;
+                        if (even)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                                         "r"((unsigned)__cvta_generic_to_shared(buf)), "r"((unsigned)even * 8u)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");     // one group per chunk, empty or not
+                        if (len & 1) dst[len - 1] = buf[len - 1];
+                    }
+#else
+                    for (int e = lane; e < len; e += 32) dst[e] = buf[e];
+#endif
+                WARP_PHASE_END
+                ++gen;
+            }
+        WARP_SECTION_END
+        CTA_SYNC                                // every warp is done composing from gs / dbar
+        if (bn >= 0 && bn != b) {
+            CTA_PHASE(tid)
+#if SCP_DEVICE_BUILD
+                if (prefetch) {
+#pragma unroll
+                    for (int s = 0; s < SCP_ASM_PF; ++s) {
+                        const int e = tid + s * cta.nt;
+                        if (e < sm.nstage) gs[e] = pf[s];
+                    }
+                } else
+#endif
+                for (int e = tid; e < sm.nstage; e += cta.nt)
+                    gs[e] = scp_asm_stage_src(d, bn, e, g, cterm, ubar, dsafe, dsafe_obst, obst);
+            CTA_PHASE_END
+        }
+    }
 }

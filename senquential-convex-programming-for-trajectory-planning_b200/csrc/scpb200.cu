@@ -112,15 +112,13 @@ __global__ void __launch_bounds__(256) k_assemble(scpb200_dims d, scpb200_params
 {
     extern __shared__ double sh[];
     Cta cta = {(int)blockDim.x};
-    for (int e = threadIdx.x; e < SCP_ASM_ZBUF; e += blockDim.x) sh[e] = 0.0;      // the zero source of the bulk stores
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                     // -> visible to the async proxy
-    __syncthreads();
-    const long nitems = (long)d.B * nparts;
-    for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-        scp_assemble_instance(cta, d, p, (int)(w / nparts), (int)(w % nparts), nparts, g, cterm, H, qv, ubar, dsafe, dsafe_obst,
-                              obst, P, q, A, bvec, lb, ub, sh);
-        __syncthreads();
-    }
+    ScpAsmMem sm;
+    scp_asm_carve(sm, sh, d.nVeh, d.Hp, d.nObst, (int)blockDim.x >> 5);
+    scp_asm_rowinfo(cta, d.nVeh, d.Hp, d.nObst, sm.rowinfo);
+    scp_assemble_items(cta, d, p, (long)blockIdx.x, (long)gridDim.x, (long)d.B * nparts, nparts, g, cterm, H, qv, ubar, dsafe,
+                       dsafe_obst, obst, P, q, A, bvec, lb, ub, sm);
+    // the chunk buffers must outlive the bulk reads in flight
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) k_evaluate(scpb200_dims d, scpb200_params p, const double *g, const double *cterm,
@@ -514,22 +512,27 @@ extern "C" int scpb200_assemble_dense(const scpb200_dims *d, const scpb200_param
     if (!p || !g || !cterm || !H || !qv || !ubar || !dsafe || !P || !q || !A || !b || !lb || !ub)
         return set_err(SCPB200_ERR_ARG, "scpb200_assemble_dense: NULL argument");
     if (d->nObst && (!dsafe_obst || !obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
+    if ((reinterpret_cast<size_t>(P) | reinterpret_cast<size_t>(A)) & 15)
+        return set_err(SCPB200_ERR_ARG, "scpb200_assemble_dense: P and A must be 16-byte aligned (bulk stores)");
     if (d->B == 0) return 0;
     DevInfo di;
     rc = dev_info(&di);
     if (rc) return rc;
     const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
-    const size_t smem = ((size_t)SCP_ASM_ZBUF + (size_t)n * 2 + (size_t)mc * 2 + mc + (size_t)n * 2 + n + 16) * 8;
+    (void)n; (void)mc;
+    const int asm_threads = env_int("SCPB200_ASM_THREADS", 256);
+    ScpAsmMem am;
+    const size_t smem = scp_asm_carve(am, (double *)0, d->nVeh, d->Hp, d->nObst, asm_threads / 32) * 8;
     if (smem > (size_t)di.smem_optin) return set_err(SCPB200_ERR_SIZE, "assemble: row data exceed shared memory");
     CUDA_TRY(cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble, 256, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_assemble, asm_threads, smem));
     if (occ < 1) occ = 1;
-    const int nparts = mc >= 16 ? env_int("SCPB200_ASM_PARTS", 4) : 1;      // work items per instance (row ranges)
+    const int nparts = mc >= 16 ? env_int("SCPB200_ASM_PARTS", 2) : 1;      // work items per instance (row ranges)
     long grid = (long)di.sms * occ;
     if (env_int("SCPB200_ASM_GRID_ITEMS", 0)) grid = (long)d->B * nparts;    // one CTA per work item: the hardware scheduler balances
     if (grid > (long)d->B * nparts) grid = (long)d->B * nparts;
-    k_assemble<<<(int)grid, 256, smem, (cudaStream_t)stream>>>(*d, *p, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q,
+    k_assemble<<<(int)grid, asm_threads, smem, (cudaStream_t)stream>>>(*d, *p, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q,
                                                                A, b, lb, ub, nparts);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -52,12 +52,17 @@ extern "C" int emu_assemble_dense(const scpb200_dims *d, const scpb200_params *p
 {
     Cta *cta = new_cta();
     const int n = d->nVeh * d->Hp, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
-    std::vector<double> sh((size_t)SCP_ASM_ZBUF + (size_t)n * 5 + (size_t)mc * 3 + 32);
-    const int nparts = mc >= 16 ? 4 : 1;
-    for (int bi = 0; bi < d->B; ++bi)
-        for (int part = 0; part < nparts; ++part)
-            scp_assemble_instance(*cta, *d, *p, bi, part, nparts, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst, P, q, A, b,
-                                  lb, ub, sh.data());
+    (void)n;
+    ScpAsmMem am;
+    const size_t nd = scp_asm_carve(am, (double *)0, d->nVeh, d->Hp, d->nObst, cta->nt / 32);
+    std::vector<double> sh(nd + 32, 1e300);                 // poisoned: every element written must come from the composer
+    scp_asm_carve(am, sh.data(), d->nVeh, d->Hp, d->nObst, cta->nt / 32);
+    scp_asm_rowinfo(*cta, d->nVeh, d->Hp, d->nObst, am.rowinfo);
+    const int nparts = mc >= 16 ? 2 : 1;
+    // two interleaved "CTAs" (stride 2) so that items of different instances follow each other, as on the device
+    for (int first = 0; first < 2; ++first)
+        scp_assemble_items(*cta, *d, *p, first, 2, (long)d->B * nparts, nparts, g, cterm, H, qv, ubar, dsafe, dsafe_obst, obst,
+                           P, q, A, b, lb, ub, am);
     free(cta);
     return 0;
 }
