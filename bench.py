@@ -181,6 +181,16 @@ def workload_config(args, B_per_gpu, note=None):
 
 
 # ---------------------------------------------------------------------------------------------------- product arm
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture
+    summary (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that kernel was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -310,7 +320,8 @@ def run_product(args):
         peaks, how = measured_peaks()
         abytes = assembly_bytes_per_qp(nVeh, Hp) * B
         asm = {"bound": "hbm", "kernel": "k_assemble", "achieved": abytes / (ams * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+               "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": ncu_traffic("k_assemble"),
+               "peak_source": how,
                "ms_per_launch": ams, "algorithmic_bytes_per_launch": abytes}
         del outbuf
 
@@ -332,9 +343,10 @@ def run_product(args):
     if rank == 0:
         value = qps_all / t_max
         fit = algorithmic_flops_per_ipm_iteration(nVeh, Hp)
-        # dominant kernel: k_scp_solve (FP64 pipe).  Flops per launch = F_it x (IPM iterations + 1 start-point
-        # factorisation per QP) of that launch; duration = CUDA events around the launch on its stream.
-        fl = fit * (ipm_per_step + qp_per_step)
+        # dominant kernel: k_scp_solve (FP64 pipe).  Flops per launch = F_it x IPM iterations executed in that launch
+        # (the start-point factorisations of cold-started QPs are not counted: conservative); duration = CUDA events
+        # around the launch on its stream.
+        fl = fit * ipm_per_step
         ach = float(fl.sum() / (solve_ms.sum() * 1e-3) / 1e12)
         fp64_peak = float(os.environ.get("SCPB200_FP64_PEAK_TFLOPS", "37.0"))
         line = {
@@ -345,8 +357,9 @@ def run_product(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak, "traffic": None,
-                         "peak_source": "nominal B200 FP64 (HGX datasheet 296 TF / 8 GPUs); not in MEASURED_PEAKS.json",
+                         "frac": ach / fp64_peak, "traffic": ncu_traffic("k_scp_solve"),
+                         "peak_source": "measured on this pool's B200 (tools/microbench_dmma.cu: DMMA m8n8k4 37.0 TFLOP/s, "
+                                        "DFMA 36.5; profiles/r01_microbench*.txt); MEASURED_PEAKS.json has no FP64 entry",
                          "algorithmic_flops_per_ipm_iteration": fit, "solve_share_of_step": float(solve_ms.sum() / step_ms.sum())},
             "roofline_assembly": asm,
             "stats": {"qps_total": qps_all, "ipm_iterations_total": ipm_all, "qp_per_instance_step": qps_all / (world * B * args.steps),

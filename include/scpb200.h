@@ -157,6 +157,21 @@ int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *p, const do
                         const double *veh, double T, int32_t steps, int32_t nsub, double *out, void *stream);
 
 /*
+ * The caller's half of one MPC step — replaces main.py:104-109 (dynamic steering limit),
+ * :164-174 (clamp of the controller output to +-uMax and the rate limit duLim) and :176-191 (plant integration over
+ * one sample time, Model.py:89-115, with the actuation delay of main.py:176-181: during step i the plant runs with
+ * the command of step i-1).  The reference integrates with dopri5 at 1e-8; here RK4 with nsub substeps (64 gives
+ * < 1e-9 m).  Process noise as in scpb200_ode_predict (p->noise_sigma, Philox keyed by instance / vehicle / counter).
+ *   in    : veh[B,nVeh,5] (Lf, Lr used), U[B,Hp,nVeh] controller output (K4), mech_limit, lat_acc_limit, duLim, T = dt
+ *   in/out: x_meas[B,nVeh,6] state at the step's first tick -> at its last tick (the next x_measured);
+ *           u_act[B,nVeh] command being actuated (u_path[:, -1] = Iter.u0) -> clamped U[0] (the next Iter.u0)
+ *   out   : u_max_out[B,nVeh] (Iter.uMax; may be NULL), U_clamped[B,Hp,nVeh] (controlPredictions; may be NULL)
+ */
+int scpb200_plant_step(const scpb200_dims *d, const scpb200_params *p, const double *veh, const double *U,
+                       double mech_limit, double lat_acc_limit, double duLim, double T, int32_t nsub, double *x_meas,
+                       double *u_act, double *u_max_out, double *U_clamped, void *stream);
+
+/*
  * Closed-loop advance on the controller's own linear model (MPC_Iter.py:94-97): x0 <- Ad x0 + Bd u + Ed,
  * u0 <- u, with u = U[b,0,v] clamped to |u| <= uMax and |u - u0| <= duLim as main.py:164-168 does.
  * Used by the synthetic benchmark to close the loop between MPC steps without leaving the device.

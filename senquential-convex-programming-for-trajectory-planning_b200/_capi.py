@@ -62,6 +62,8 @@ PROTOTYPES = {
     "scpb200_qcqp_evaluate": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 16,
     "scpb200_forward_u": [C.POINTER(Dims)] + [_P] * 6,
     "scpb200_ode_predict": [C.POINTER(Dims), C.POINTER(Params), _P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P, _P],
+    "scpb200_plant_step": [C.POINTER(Dims), C.POINTER(Params), _P, _P, C.c_double, C.c_double, C.c_double, C.c_double,
+                           C.c_int32, _P, _P, _P, _P, _P],
     "scpb200_advance_linear": [C.POINTER(Dims), _P, _P, C.c_double, C.c_double, _P, _P, _P],
     "scpb200_qp_solve_dense": [C.POINTER(Dims), C.POINTER(Params), C.c_int32, C.c_int32] + [_P] * 13,
     "scpb200_scp_solve": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 19,

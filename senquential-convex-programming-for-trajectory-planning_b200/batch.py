@@ -200,6 +200,35 @@ class BatchSCP:
                   "scpb200_advance_linear")
         self.kernel_launches += 1
 
+    def plant_step(self, x_meas: torch.Tensor, u_act: torch.Tensor, mech_limit: float, lat_acc_limit: float, duLim: float,
+                   T: Optional[float] = None, nsub: int = 64, want_clamped: bool = False):
+        """The caller's half of an MPC step (main.py:104-109, 164-191) on device: clamp U (K4 output) to the dynamic
+        steering limit and the rate limit, integrate the plant over one sample time with the command being actuated.
+        x_meas[B,nVeh,6] and u_act[B,nVeh] are float64 device tensors updated IN PLACE; returns (uMax, U_clamped|None)."""
+        assert x_meas.is_cuda and u_act.is_cuda and x_meas.dtype == torch.float64 and u_act.dtype == torch.float64
+        assert x_meas.is_contiguous() and u_act.is_contiguous()
+        umax = torch.empty(self.B, self.nVeh, dtype=torch.float64, device=self.device)
+        uc = torch.empty_like(self.U) if want_clamped else None
+        with torch.cuda.device(self.device):
+            check(self.lib.scpb200_plant_step(
+                C.byref(self.dims), C.byref(self.params), _ptr(self.veh), _ptr(self.U), C.c_double(mech_limit),
+                C.c_double(lat_acc_limit), C.c_double(duLim), C.c_double(self.params.dt if T is None else T),
+                C.c_int32(nsub), _ptr(x_meas), _ptr(u_act), _ptr(umax), _ptr(uc), self._stream()), "scpb200_plant_step")
+        self.kernel_launches += 1
+        return umax, uc
+
+    def mpc_step(self, x_meas: torch.Tensor, u_act: torch.Tensor, mech_limit: float, lat_acc_limit: float, duLim: float,
+                 delay: float, nsub_delay: int = 16, nsub_plant: int = 64):
+        """One whole MPC step of main.py:98-191 with every stage on the device and no host round trip:
+        IterClass delay compensation (MPC_Iter.py:25-33) -> K1 -> K4 -> clamp + plant.  `delay` = delay_x + dt + delay_u.
+        x_meas / u_act are updated in place; the warm start is the previous solution left in self.u (SCP_controller.py:42-43)."""
+        pred = self.ode_predict(x_meas, u_act, delay, steps=2, nsub=nsub_delay * 9)
+        self.x0.copy_(pred[:, :, 1, :])
+        self.u0.copy_(u_act)
+        self.setup()
+        self.solve()
+        return self.plant_step(x_meas, u_act, mech_limit, lat_acc_limit, duLim, nsub=nsub_plant)
+
     def ode_predict(self, x: torch.Tensor, u_ref: torch.Tensor, T: float, steps: int = 10, nsub: int = 16):
         """Delay-compensation prediction (MPC_Iter.py:25-33) for the batch; returns [B,nVeh,steps,6]."""
         x, u_ref = self._dev(x), self._dev(u_ref)

@@ -373,6 +373,40 @@ SCP_HDFN void scp_ode_predict_vehicle(const double *x_in, double u_ref, double L
     }
 }
 
+// ================================================================================================ plant step
+// The caller's half of one MPC step (main.py), for one vehicle:
+//   :104-109  uMax = min(mechanicalSteeringLimit, atan(lateralAccelerationLimit (Lf+Lr) / speed^2)) at the measured state
+//   :164-174  clamp of the controller output: U[0] to +-uMax and u0 +- duLim, U[j] to +-uMax and U[j-1] +- duLim
+//   :176-191  plant integration over one sample time.  The command computed at step i reaches the actuator
+//             ticks_per_sim + ticks_delay_u ticks later, so during step i the plant runs with the PREVIOUS command
+//             (controlPathFullRes at the step's last tick = u_path[:, -1] = Iter.u0); the state main.py measures at
+//             the next step is the integral over dt with that command held constant.
+// The reference integrates with dopri5 (rtol = atol = 1e-8); here classical RK4 with nsub substeps.
+// x (6 states) and u_act (the command being actuated) are updated in place; U points at U[b, 0, v], stride nVeh.
+SCP_HDFN void scp_plant_step_vehicle(double *x, double *u_act, const double *U, double *Uc, int Hp, int nVeh, double Lf,
+                                     double Lr, double mech_limit, double lat_acc_limit, double duLim, double T, int nsub,
+                                     double noise_sigma, uint64_t seed, uint32_t instance, uint32_t vehicle,
+                                     uint32_t noise_counter, double *uMax_out)
+{
+    const double speed = x[3];
+    const double uMax = fmin(mech_limit, atan(lat_acc_limit * (Lf + Lr) / (speed * speed)));
+    const double u0 = *u_act;
+    double prev = u0, first = 0.0;
+    for (int j = 0; j < (Uc ? Hp : 1); ++j) {
+        double uj = U[(size_t)j * nVeh];
+        uj = fmin(uj, uMax); uj = fmax(uj, -uMax);
+        uj = fmin(uj, prev + duLim); uj = fmax(uj, prev - duLim);
+        if (Uc) Uc[(size_t)j * nVeh] = uj;
+        if (j == 0) first = uj;
+        prev = uj;
+    }
+    double out[12];
+    scp_ode_predict_vehicle(x, u0, Lf, Lr, T, 2, nsub, noise_sigma, seed, instance, vehicle, noise_counter, out);
+    for (int i = 0; i < 6; ++i) x[i] = out[6 + i];
+    *u_act = first;
+    if (uMax_out) *uMax_out = uMax;
+}
+
 // ================================================================================================ linear advance
 // x <- Ad x + Bd u_applied + Ed, u0 <- u_applied with u_applied = U[0, v] clamped as main.py:164-168 does
 // (|u| <= uMax, |u - u0| <= duLim).  This is the linearised plant the controller itself predicts with

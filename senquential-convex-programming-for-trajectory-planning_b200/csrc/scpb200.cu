@@ -179,6 +179,26 @@ __global__ void __launch_bounds__(128) k_ode_predict(scpb200_dims d, scpb200_par
     }
 }
 
+__global__ void __launch_bounds__(128) k_plant_step(scpb200_dims d, scpb200_params p, const double *veh, const double *U,
+                                                    double mech_limit, double lat_acc_limit, double duLim, double T, int nsub,
+                                                    double *x_meas, double *u_act, double *u_max_out, double *U_clamped)
+{
+    const int tot = d.B * d.nVeh;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int b = e / d.nVeh, v = e - b * d.nVeh;
+        double x[6];
+        for (int i = 0; i < 6; ++i) x[i] = x_meas[(size_t)e * 6 + i];
+        double ua = u_act[e];
+        scp_plant_step_vehicle(x, &ua, U + (size_t)b * d.Hp * d.nVeh + v,
+                               U_clamped ? U_clamped + (size_t)b * d.Hp * d.nVeh + v : (double *)0, d.Hp, d.nVeh,
+                               veh[(size_t)e * 5], veh[(size_t)e * 5 + 1], mech_limit, lat_acc_limit, duLim, T, nsub,
+                               p.noise_sigma, p.seed, p.instance0 + (uint32_t)b, (uint32_t)v, p.noise_counter,
+                               u_max_out ? u_max_out + e : (double *)0);
+        for (int i = 0; i < 6; ++i) x_meas[(size_t)e * 6 + i] = x[i];
+        u_act[e] = ua;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_advance_linear(scpb200_dims d, const double *abe, const double *U, double uMax,
                                                         double duLim, double *x0, double *u0)
 {
@@ -588,6 +608,23 @@ extern "C" int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *
     const int tot = d->B * d->nVeh;
     const int grid = (tot + 63) / 64 < 65535 ? (tot + 63) / 64 : 65535;
     k_ode_predict<<<grid, 64, 0, (cudaStream_t)stream>>>(*d, *p, x, u_ref, veh, T, steps, nsub, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_plant_step(const scpb200_dims *d, const scpb200_params *p, const double *veh, const double *U,
+                                  double mech_limit, double lat_acc_limit, double duLim, double T, int32_t nsub,
+                                  double *x_meas, double *u_act, double *u_max_out, double *U_clamped, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !veh || !U || !x_meas || !u_act || nsub < 1 || !(T > 0.0))
+        return set_err(SCPB200_ERR_ARG, "scpb200_plant_step: bad argument");
+    if (d->B == 0) return 0;
+    const int tot = d->B * d->nVeh;
+    const int grid = (tot + 63) / 64 < 65535 ? (tot + 63) / 64 : 65535;
+    k_plant_step<<<grid, 64, 0, (cudaStream_t)stream>>>(*d, *p, veh, U, mech_limit, lat_acc_limit, duLim, T, nsub, x_meas, u_act,
+                                                        u_max_out, U_clamped);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -160,6 +160,21 @@ extern "C" int emu_ode_predict(const scpb200_dims *d, const scpb200_params *p, c
     return 0;
 }
 
+extern "C" int emu_plant_step(const scpb200_dims *d, const scpb200_params *p, const double *veh, const double *U,
+                              double mech_limit, double lat_acc_limit, double duLim, double T, int32_t nsub, double *x_meas,
+                              double *u_act, double *u_max_out, double *U_clamped)
+{
+    for (int e = 0; e < d->B * d->nVeh; ++e) {
+        const int b = e / d->nVeh, v = e % d->nVeh;
+        scp_plant_step_vehicle(x_meas + (size_t)e * 6, u_act + e, U + (size_t)b * d->Hp * d->nVeh + v,
+                               U_clamped ? U_clamped + (size_t)b * d->Hp * d->nVeh + v : (double *)0, d->Hp, d->nVeh,
+                               veh[(size_t)e * 5], veh[(size_t)e * 5 + 1], mech_limit, lat_acc_limit, duLim, T, nsub,
+                               p->noise_sigma, p->seed, p->instance0 + (uint32_t)b, (uint32_t)v, p->noise_counter,
+                               u_max_out ? u_max_out + e : (double *)0);
+    }
+    return 0;
+}
+
 extern "C" size_t emu_scp_shared_bytes(int nVeh, int Hp, int nObst, int S_in_shared)
 {
     size_t shu, glu;

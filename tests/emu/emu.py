@@ -130,6 +130,17 @@ def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=N
     return dict(u=u, traj=traj, U=U, log=log, scp_iters=si, ipm_iters=ii, status=st, obj=obj, max_violation=mv)
 
 
+def plant_step(x_meas, u_act, veh, U, mech_limit, lat_acc_limit, duLim, T, nsub, params):
+    """returns (x_next, u_next, uMax, U_clamped)"""
+    x, ua, veh, U = _c(x_meas).copy(), _c(u_act).copy(), _c(veh), _c(U)
+    B, Hp, nVeh = U.shape
+    d = Dims(B, nVeh, Hp, 0, 2)
+    umax, uc = np.zeros((B, nVeh)), np.zeros((B, Hp, nVeh))
+    lib().emu_plant_step(C.byref(d), C.byref(params), _d(veh), _d(U), C.c_double(mech_limit), C.c_double(lat_acc_limit),
+                         C.c_double(duLim), C.c_double(T), C.c_int32(nsub), _d(x), _d(ua), _d(umax), _d(uc))
+    return x, ua, umax, uc
+
+
 def ode_predict(x, u_ref, veh, T, steps, nsub, params):
     x, u_ref, veh = _c(x), _c(u_ref), _c(veh)
     B, nVeh = x.shape[0], x.shape[1]

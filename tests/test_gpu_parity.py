@@ -322,6 +322,47 @@ def test_ode_predict_and_linear_advance(mods, oracle):
         assert abs(host(bs.u0)[0, v] - ua) < 1e-15
 
 
+def test_plant_step_and_device_resident_closed_loop(mods):
+    """SURVEY 8f rank 1: (a) scpb200_plant_step against the reference's own run (next measured state, clamped command);
+    (b) the whole MPC step on device (delay compensation -> K1 -> K4 -> clamp + plant, no host round trip) run free
+    for 50 steps from the scenario's initial state: collision-free, converges to the reference's end state, and equals
+    the reference's trajectory up to the first symmetric conflict (where its own solver noise decides the branch)."""
+    torch = mods["torch"]
+    R = load_golden("circle8_hp10_run.npz")
+    G0 = load_golden("circle8_hp10_step0.npz")
+    mech, lat, du, dt = (float(R[k]) for k in ("sc_mechanicalSteeringLimit", "sc_lateralAccelerationLimit", "sc_duLim", "sc_dt"))
+    n = R["x_measured"].shape[0] - 2            # the last transition is truncated at the end of the simulated timespan
+    bs = make_batch(mods, G0, B=n)
+    bs.U.copy_(torch.as_tensor(R["u_final"][:n].reshape(n, 8, 10).transpose(0, 2, 1).copy()))
+    x = torch.as_tensor(R["x_measured"][:n].copy()).cuda()
+    ua = torch.as_tensor(R["u0"][:n].copy()).cuda()
+    umax, uc = bs.plant_step(x, ua, mech, lat, du, want_clamped=True)
+    assert np.abs(host(x) - R["x_measured"][1:n + 1]).max() < 2e-7
+    assert np.abs(host(ua) - R["u0"][1:n + 1]).max() < 1e-12
+    assert np.abs(host(uc) - R["U_clamped"][:n]).max() < 1e-12
+    # (b) free-running closed loop, 4 copies of the scenario in one batch (identical results expected)
+    B = 4
+    bs = make_batch(mods, G0, B=B)
+    x = torch.as_tensor(np.repeat(R["sc_x_init"][None], B, 0).copy()).cuda()
+    ua = torch.as_tensor(np.repeat(R["sc_u_init"][None], B, 0).copy()).cuda()
+    delay = float(R["sc_delay_x"]) + dt + float(R["sc_delay_u"])
+    path, feas = [host(x).copy()], []
+    for i in range(50):
+        bs.mpc_step(x, ua, mech, lat, du, delay)
+        path.append(host(x).copy())
+        feas.append((host(bs.status) & 8) == 0)
+    path = np.stack(path)                                                       # [51, B, nVeh, 6]
+    assert np.abs(path - path[:, :1]).max() == 0.0                              # copies agree bit for bit
+    ref = R["vehiclePath_step_ends"].transpose(2, 1, 0)                         # [51, nVeh, 6]
+    assert np.abs(path[:6, 0] - ref[:6]).max() < 1e-4                           # before the symmetric conflict: 1e-4 m
+    assert np.all(feas)
+    pos = path[:, 0, :, :2]
+    dmin = min(np.linalg.norm(pos[:, a] - pos[:, b], axis=1).min() for a in range(8) for b in range(a + 1, 8))
+    assert dmin > 3.0                                                           # reference run: 3.0661 m
+    goal = R["sc_poly"][:, 1, :]
+    assert np.linalg.norm(pos[-1] - goal, axis=1).max() < np.linalg.norm(ref[-1, :, :2] - goal, axis=1).max() + 1.0
+
+
 def test_noise_is_keyed_per_instance_and_reproducible(mods, oracle):
     G = load_golden("circle8_hp10_step10.npz")
     bs = make_batch(mods, G, B=4, noise_sigma=3e-6, seed=99, instance0=5, noise_counter=2)

@@ -228,3 +228,21 @@ def test_scp_kernel_park_and_resume_is_bit_identical(oracle, quantum, monkeypatc
     assert a["scp_iters"][0] > quantum
     for k in ("u", "traj", "U", "log", "scp_iters", "ipm_iters", "status", "obj", "max_violation"):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+def test_plant_step_vs_reference_run(oracle):
+    """Clamp + plant integration of main.py:104-109, 164-191 against the reference's own 50-step run: from the
+    reference's measured state, actuated command and raw controller output of step i, the next measured state
+    (dopri5 at 1e-8 in the reference) and the clamped command."""
+    R = load_golden("circle8_hp10_run.npz")
+    G0 = load_golden("circle8_hp10_step0.npz")
+    n = R["x_measured"].shape[0] - 2            # the last transition is truncated at the end of the simulated timespan
+    veh = np.repeat(np.stack([G0["sc_Lf"], G0["sc_Lr"], G0["sc_Q"], G0["sc_Q_final"], G0["sc_R"]], axis=1)[None], n, 0)
+    U = R["u_final"][:n].reshape(n, 8, 10).transpose(0, 2, 1)                  # U[b, k, v] = u[v*Hp + k]
+    x, ua, umax, uc = emu.plant_step(R["x_measured"][:n], R["u0"][:n], veh, U, float(R["sc_mechanicalSteeringLimit"]),
+                                     float(R["sc_lateralAccelerationLimit"]), float(R["sc_duLim"]), float(R["sc_dt"]), 64,
+                                     params_for(G0))
+    assert np.abs(x - R["x_measured"][1:n + 1]).max() < 2e-7
+    assert np.abs(ua - R["u0"][1:n + 1]).max() < 1e-12
+    assert np.abs(uc - R["U_clamped"][:n]).max() < 1e-12
+    assert np.abs(umax - float(R["sc_mechanicalSteeringLimit"])).max() < 1e-15    # v = 4 m/s: the mechanical limit binds
