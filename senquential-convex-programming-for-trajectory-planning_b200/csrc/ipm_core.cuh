@@ -41,6 +41,7 @@ struct IpmCtl {
     double *snap;
     double snap_relgap;
     int warm;
+    int snap_min_iter;   // tuning: the saved iterate is not taken before this iteration
 };
 
 // Pointers into the CTA's working set.  n1p = n1 rounded up to the tile size; vectors of length n1p have
@@ -565,7 +566,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         if (pres <= ctl.feastol && dres <= ctl.feastol &&
             (gap <= ctl.abstol || (relgap >= 0.0 && relgap <= ctl.reltol))) { status = 0; break; }
         if (iters == ctl.max_iter) break;
-        if (ctl.snap && !snap_saved && relgap >= 0.0 && relgap <= ctl.snap_relgap) {
+        if (ctl.snap && !snap_saved && iters >= ctl.snap_min_iter && relgap >= 0.0 && relgap <= ctl.snap_relgap) {
             ipm_snapshot(cta, m, ctl.snap, true);
             snap_saved = 1;
         }

@@ -710,6 +710,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     ctl.snap = (io.snap && p.qp_warm_start) ? io.snap + (size_t)b * ipm_snap_doubles(m.n1p, mc) : 0;
     ctl.snap_relgap = p.qp_warm_relgap;
     ctl.warm = 0;
+    ctl.snap_min_iter = p.qp_warm_min_iter;
     int snap_valid = 0;
 
     PairOp op;
@@ -720,6 +721,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
 
     double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
     const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance
+    const int snap_carried = stB ? (int)SCP_LD_COHERENT(stB + 6) : 0;
 
     // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
     CTA_PHASE(tid)
@@ -744,6 +746,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra, p.constraint_tol,
                      p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
         obj0 = ev.obj; mv0 = ev.max_violation;
+        snap_valid = snap_carried;
     } else {
         obj0 = SCP_LD_COHERENT(stB + 0); mv0 = SCP_LD_COHERENT(stB + 1);
         it = it_resume; ipm_total = (int)SCP_LD_COHERENT(stB + 3); st = (int)SCP_LD_COHERENT(stB + 4);
@@ -837,6 +840,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             if (io.status) io.status[b] = st;
             if (io.obj) io.obj[b] = ev.obj;
             if (io.max_violation) io.max_violation[b] = ev.max_violation;
+            if (stB) stB[6] = (double)snap_valid;          // the iterate a following call may start from (qp_warm_carry)
         }
     CTA_PHASE_END
     return true;
@@ -854,7 +858,7 @@ SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc,
     IpmCtl ctl;
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
-    ctl.snap = 0; ctl.snap_relgap = 0.0; ctl.warm = 0;
+    ctl.snap = 0; ctl.snap_relgap = 0.0; ctl.warm = 0; ctl.snap_min_iter = 0;
     DenseOp op;
     op.n1 = n1; op.mc = mc;
     op.P = io.P + (size_t)b * n1 * n1;

@@ -50,6 +50,8 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->qp_warm_start = 1;
     p->qp_warm_relgap = 1.0;
     p->qp_warm_max_iter = 30;
+    p->qp_warm_min_iter = 2;
+    p->qp_warm_carry = 0;
 }
 
 extern "C" int scpb200_device_count(void)
@@ -261,7 +263,7 @@ __device__ __forceinline__ int queue_pop(const WorkQueue &q)
 // `order` (optional) lists the instances by descending expected work.  The first `npinned` of them are the likely
 // stragglers: they are started first and never parked, so the longest chain of QPs of the step runs without waiting;
 // everything else shares the remaining CTAs round-robin.
-__global__ void k_queue_init(int B, const int32_t *order, int npinned, WorkQueue q, double *state)
+__global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_snap, WorkQueue q, double *state)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < q.cap) q.slots[i] = i < B ? (order ? order[i] : i) : -1;
@@ -269,6 +271,7 @@ __global__ void k_queue_init(int B, const int32_t *order, int npinned, WorkQueue
         const int b = order ? order[i] : i;
         state[(size_t)b * SCP_STATE_W + 2] = 0.0;                  // it = 0: a fresh instance
         state[(size_t)b * SCP_STATE_W + 5] = (order && i < npinned) ? 1.0 : 0.0;
+        if (!keep_snap) state[(size_t)b * SCP_STATE_W + 6] = 0.0;    // no warm-start iterate from an earlier call
     }
     if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
 }
@@ -715,7 +718,8 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     io.quantum = env_int("SCPB200_QUANTUM", 1);
     io.snap = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
     double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d));
-    k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2), q, io.state);
+    k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2),
+                                                      p->qp_warm_start && p->qp_warm_carry, q, io.state);
     CUDA_TRY(cudaGetLastError());
     if (pl.all_shared)
         k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, q, gws, pl.gl_stride, pl.sh_lim,

@@ -28,6 +28,9 @@ ap.add_argument("--step-hi", type=int, default=7)
 ap.add_argument("--assemble", action="store_true")
 ap.add_argument("--warm", type=int, default=-1)
 ap.add_argument("--warm-relgap", dest="wrg", type=float, default=-1.0)
+ap.add_argument("--snap-min-iter", dest="smi", type=int, default=0)
+ap.add_argument("--carry", type=int, default=0)
+ap.add_argument("--warm-max-iter", dest="wmi", type=int, default=0)
 args = ap.parse_args()
 
 cb = scen.circle_batch(args.batch, Hp=args.hp, step_lo=args.step_lo, step_hi=args.step_hi)
@@ -36,6 +39,10 @@ capi.load().scpb200_default_params(C.byref(p))
 p.max_scp_iter = args.msi
 if args.warm >= 0:
     p.qp_warm_start = args.warm
+p.qp_warm_min_iter = args.smi if args.smi else p.qp_warm_min_iter
+p.qp_warm_carry = args.carry
+if args.wmi > 0:
+    p.qp_warm_max_iter = args.wmi
 if args.wrg > 0:
     p.qp_warm_relgap = args.wrg
 bs = batch.BatchSCP(args.batch, 8, args.hp, params=p)
