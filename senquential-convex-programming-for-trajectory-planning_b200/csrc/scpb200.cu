@@ -276,13 +276,15 @@ __global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_
     if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
 }
 
+// The body of k_scp_solve for given dimensions.  Called with run-time dims, and — for the shapes BASELINE.json names —
+// with literal dims, so that after inlining the compiler folds every index computation (n, n1, tile counts, divisions
+// by Hp) into constants and unrolls the short loops (the kernel executes ~20 instructions of addressing and loop
+// control per FP64 operation in its generic form).
 template <bool ALL_SHARED>
-__global__ void __launch_bounds__(SCP_MAX_THREADS, SCP_MIN_CTAS)
-k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws, size_t gl_stride, size_t sh_lim,
-            int alpha_slots, int want_H)
+__device__ __forceinline__ void scp_solve_body(const scpb200_dims &d, const scpb200_params &p, const ScpIO &io, const WorkQueue &q,
+                                               double *gws, size_t gl_stride, size_t sh_lim, int alpha_slots, int want_H,
+                                               double *sh, int *slot)
 {
-    extern __shared__ double sh[];
-    __shared__ int slot;
     Cta cta = {(int)blockDim.x};
     ScpBump bp = scp_bump(sh, sh_lim, ALL_SHARED ? (double *)0 : gws + (size_t)blockIdx.x * gl_stride, ALL_SHARED);
     ScpMem s;
@@ -291,10 +293,10 @@ k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws
         if (threadIdx.x == 0) {
             const int b = queue_pop(q);
             __threadfence();                       // acquire: the parked state written by the CTA that pushed b
-            slot = b;
+            *slot = b;
         }
         __syncthreads();
-        const int b = slot;
+        const int b = *slot;
         if (b < 0) break;
         const bool done = scp_solve_instance(cta, d, p, b, io, s);
         __threadfence();                           // release: every thread's writes of this invocation ...
@@ -304,6 +306,27 @@ k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws
             else queue_push(q, b);
         }
     }
+}
+
+#ifndef SCP_SPECIALISE
+#define SCP_SPECIALISE 1
+#endif
+template <bool ALL_SHARED>
+__global__ void __launch_bounds__(SCP_MAX_THREADS, SCP_MIN_CTAS)
+k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws, size_t gl_stride, size_t sh_lim,
+            int alpha_slots, int want_H)
+{
+    extern __shared__ double sh[];
+    __shared__ int slot;
+#if SCP_SPECIALISE
+    if (ALL_SHARED && d.nVeh == 8 && d.Hp == 10 && d.nObst == 0 && alpha_slots == 1 && want_H == 0) {
+        scpb200_dims dc = d;
+        dc.nVeh = 8; dc.Hp = 10; dc.nObst = 0;
+        scp_solve_body<ALL_SHARED>(dc, p, io, q, gws, gl_stride, sh_lim, 1, 0, sh, &slot);
+        return;
+    }
+#endif
+    scp_solve_body<ALL_SHARED>(d, p, io, q, gws, gl_stride, sh_lim, alpha_slots, want_H, sh, &slot);
 }
 
 // Pull order for the work queue: instances sorted by DEscending expected work (longest-processing-time-first), so
