@@ -192,6 +192,69 @@ def test_scp_kernel_free_running(mods, fname):
     assert (host(bs.status)[0] & (capi.ST_SCP_MAXITER | capi.ST_INFEASIBLE)) == 0
 
 
+def _oracle_teacher(oracle, G, S, **kw):
+    tight = dict(abstol=1e-10, reltol=1e-10, feastol=1e-9)
+    O = oracle.scp_optimizer(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], float(S["gamma0"][0]), G["sc_dsafeVehicles"],
+                             G["u_warm"], dsafeExtra=float(G["sc_dsafeExtra"]), uLim=float(G["sc_uLim"]), opts=tight, **kw)
+    u0 = np.array(G["u_warm"], dtype=float).ravel().copy()
+    if abs(u0[0]) < 2.220446049250313e-16:
+        u0[0] = 2.220446049250313e-16                                   # SCP_controller.py:75-76
+    return O, np.vstack([u0[None], O["u_hist"][:-1]])
+
+
+@pytest.mark.parametrize("fname", ["circle8_hp10_step6.npz", "circle8_hp20_step7.npz"])
+def test_trust_region_vs_oracle(mods, oracle, fname):
+    """BASELINE config 4's extension (trust_radius folded into the box), teacher-forced against the oracle's own
+    trust-region SCP run, then free-running with a raised iteration cap."""
+    G = load_golden(fname)
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    S = oracle.mpc_setup(x0, u0, veh, poly, Hp=int(G["sc_Hp"]), dt=float(G["sc_dt"]))
+    rho = 0.2 * float(G["sc_uLim"])
+    O, ubars = _oracle_teacher(oracle, G, S, trust_radius=rho, max_scp_iter=12)
+    bs = make_batch(mods, G, B=len(ubars), max_scp_iter=1, trust_radius=rho)
+    bs.load_inputs(u=ubars)
+    bs.controller_step()
+    u = host(bs.u)
+    assert np.abs(u - O["u_hist"]).max() < 1e-6
+    assert (np.abs(u - ubars) <= rho + 1e-9).all()
+    bs = make_batch(mods, G, B=1, max_scp_iter=100, trust_radius=rho)
+    bs.load_inputs(u=G["u_warm"][None])
+    bs.controller_step()
+    assert 1 <= int(host(bs.scp_iters)[0]) <= 100 and (host(bs.status)[0] & (mods["capi"].ST_QP_MAXITER | mods["capi"].ST_QP_PIVOT)) == 0
+
+
+def test_obstacle_rows_vs_oracle(mods, oracle):
+    """Obstacle rows (SCP_controller.py:106-114, 321-326) in K4, K2 and the evaluate kernel against the
+    oracle with the same two static obstacles."""
+    capi, batch = mods["capi"], mods["batch"]
+    G = load_golden("circle3_hp10_step8.npz")
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    nVeh, Hp = int(G["sc_nVeh"]), int(G["sc_Hp"])
+    S = oracle.mpc_setup(x0, u0, veh, poly, Hp=Hp, dt=float(G["sc_dt"]))
+    pos = S["cterm"][0].reshape(nVeh, Hp, 2)
+    obst = np.stack([np.repeat((pos[0, 4] + [0.8, 0.6])[None], Hp, 0), np.repeat((pos[1, 6] + [-0.7, 0.9])[None], Hp, 0)])
+    dso = np.full((nVeh, 2), 1.2)
+    O, ubars = _oracle_teacher(oracle, G, S, dsafe_obst=dso, obst=obst, max_scp_iter=8)
+    nit = len(ubars)
+    p = capi.Params()
+    capi.load().scpb200_default_params(C.byref(p))
+    p.dt, p.uLim, p.dsafeExtra, p.max_scp_iter = float(G["sc_dt"]), float(G["sc_uLim"]), float(G["sc_dsafeExtra"]), 1
+    bs = batch.BatchSCP(nit, nVeh, Hp, nObst=2, params=p)
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    bs.load_inputs(x0=rep(x0), u0=rep(u0), veh=rep(veh), poly=rep(poly), dsafe=rep(G["sc_dsafeVehicles"][None]),
+                   dsafe_obst=rep(dso[None]), obst=rep(obst[None]), u=ubars)
+    bs.controller_step()
+    assert np.abs(host(bs.u) - O["u_hist"]).max() < 1e-6
+    # K2 with obstacle rows against the oracle's dense assembly at the same linearisation points
+    out = bs.assemble_dense(mods["torch"].as_tensor(ubars).cuda())
+    D = oracle.assemble_dense(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], ubars[1], G["sc_dsafeVehicles"],
+                              float(G["sc_dsafeExtra"]), float(G["sc_uLim"]), dsafe_obst=dso, obst=obst)
+    D = D if isinstance(D, dict) else dict(zip(("P", "q", "A", "b", "lb", "ub"), D))
+    for k in ("P", "q", "A", "b", "lb", "ub"):
+        ref = np.asarray(D[k]).reshape(host(out[k])[1].shape)
+        assert np.abs(host(out[k])[1] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), k
+
+
 def test_closed_loop_rollout_against_reference_run(mods):
     """The reference's own 50-step closed loop (golden run): at every MPC step feed the reference's measured
     state (x0, u0) and warm start; controller outputs must match where the SCP map is stable, and the number of

@@ -176,8 +176,8 @@ def test_scp_kernel_teacher_forced(oracle, fname, reverse):
 
 @pytest.mark.parametrize("slots", [0, 1, 3])
 def test_scp_kernel_pair_block_scratch_variants(oracle, slots):
-    """The normal-matrix pair blocks are formed per warp through a scratch slot; fewer slots than warps and the
-    scratch-free entry-by-entry path (large horizons) must give the same iterates."""
+    """The normal-matrix pair blocks are formed per warp on the tensor path (mode > 0) or entry by entry (mode 0, horizons
+    beyond the accumulator budget); both must give the same iterates."""
     G = load_golden("circle8_hp10_step10.npz")
     S = _setup(oracle, G)
     nit = int(G["scp_iters"])
@@ -246,3 +246,51 @@ def test_plant_step_vs_reference_run(oracle):
     assert np.abs(ua - R["u0"][1:n + 1]).max() < 1e-12
     assert np.abs(uc - R["U_clamped"][:n]).max() < 1e-12
     assert np.abs(umax - float(R["sc_mechanicalSteeringLimit"])).max() < 1e-15    # v = 4 m/s: the mechanical limit binds
+
+
+def _oracle_teacher(oracle, G, S, **kw):
+    """Linearisation points and solutions of the oracle's own SCP run with the given extensions."""
+    tight = dict(abstol=1e-10, reltol=1e-10, feastol=1e-9)
+    O = oracle.scp_optimizer(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], float(S["gamma0"][0]), G["sc_dsafeVehicles"],
+                             G["u_warm"], dsafeExtra=float(G["sc_dsafeExtra"]), uLim=float(G["sc_uLim"]), opts=tight, **kw)
+    u0 = np.array(G["u_warm"], dtype=float).ravel().copy()
+    if abs(u0[0]) < 2.220446049250313e-16:
+        u0[0] = 2.220446049250313e-16                                   # SCP_controller.py:75-76
+    ubars = np.vstack([u0[None], O["u_hist"][:-1]])
+    return O, ubars
+
+
+def test_trust_region_rows_vs_oracle(oracle):
+    """BASELINE config 4's extension: |u - ubar|_inf <= rho folded into the box (scpb200_params.trust_radius), teacher-forced
+    against the oracle's own trust-region run."""
+    G = load_golden("circle8_hp10_step6.npz")
+    S = _setup(oracle, G)
+    rho = 0.2 * float(G["sc_uLim"])
+    O, ubars = _oracle_teacher(oracle, G, S, trust_radius=rho, max_scp_iter=12)
+    nit = len(ubars)
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    r = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
+                      ubars, params_for(G, max_scp_iter=1, trust_radius=rho))
+    assert np.abs(r["u"] - O["u_hist"]).max() < 1e-6
+    assert (np.abs(r["u"] - ubars) <= rho + 1e-9).all()
+    assert np.abs(r["u"] - ubars).max() > 0.99 * rho                      # the trust region binds on this step
+
+
+def test_obstacle_rows_vs_oracle(oracle):
+    """Obstacle rows (SCP_controller.py:106-114, 321-326): two static obstacles next to the paths of the
+    3-vehicle scenario, teacher-forced against the oracle's own run with the same obstacles."""
+    G = load_golden("circle3_hp10_step8.npz")
+    S = _setup(oracle, G)
+    nVeh, Hp = int(G["sc_nVeh"]), int(G["sc_Hp"])
+    pos = S["cterm"][0].reshape(nVeh, Hp, 2)
+    obst = np.stack([np.repeat((pos[0, 4] + [0.8, 0.6])[None], Hp, 0), np.repeat((pos[1, 6] + [-0.7, 0.9])[None], Hp, 0)])
+    dso = np.full((nVeh, 2), 1.2)
+    O, ubars = _oracle_teacher(oracle, G, S, dsafe_obst=dso, obst=obst, max_scp_iter=8)
+    nit = len(ubars)
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    r = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
+                      ubars, params_for(G, max_scp_iter=1), dsafe_obst=rep(dso[None]), obst=rep(obst[None]))
+    assert np.abs(r["u"] - O["u_hist"]).max() < 1e-6
+    base = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
+                         ubars, params_for(G, max_scp_iter=1))
+    assert np.abs(r["u"] - base["u"]).max() > 1e-4                        # the obstacles matter
