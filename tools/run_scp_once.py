@@ -48,6 +48,7 @@ if args.wrg > 0:
 bs = batch.BatchSCP(args.batch, 8, args.hp, params=p)
 bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((args.batch, 8 * args.hp)))
 print("plan", bs.plan())
+TOT_IPM = TOT_QP = 0
 for s in range(args.steps):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record(); bs.setup(); e[1].record(); bs.solve(); e[2].record()
@@ -56,6 +57,7 @@ for s in range(args.steps):
     print(f"step {s}: setup {e[0].elapsed_time(e[1]):.3f} ms, solve {e[1].elapsed_time(e[2]):.3f} ms, QPs {qp}, IPM its {ipm}, "
           f"max ipm/instance {int(bs.ipm_iters.max())}, us per ipm-iteration-on-critical-path "
           f"{1e3 * e[1].elapsed_time(e[2]) / max(1, int(bs.ipm_iters.max())):.1f}")
+    TOT_IPM += ipm; TOT_QP += qp
     bs.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
 if args.assemble:
     out = bs.assemble_dense()
@@ -71,6 +73,7 @@ if os.environ.get("SCPB200_LIB", "").endswith("timers.so"):
              12: "form: forces", 13: "form: M_v(k)", 14: "form: omega+diag"}
     tot = sum(arr)
     nfac = int(bs.ipm_iters.sum()) + int(bs.scp_iters.sum())
-    print(f"phase timers, all steps (cycles of thread 0 summed over CTAs); factorisations in the last step: {nfac}")
+    nfac = TOT_IPM + TOT_QP
+    print(f"phase timers, all steps (cycles of thread 0 summed over CTAs); IPM iterations + QPs over all steps: {nfac}")
     for i in range(15):
         print(f"  {names[i]:24s} {100.0 * arr[i] / tot:5.1f}%   {arr[i] / 1e6:10.2f} Mcyc   {arr[i] / max(1, nfac):10.0f} cyc/factorisation")
