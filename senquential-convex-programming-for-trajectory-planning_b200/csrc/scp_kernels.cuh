@@ -792,7 +792,9 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         } else {
             ipm_solve(cta, op, m, ctl, &res);
         }
-        snap_valid = res.snap_saved;
+        // a warm-started QP that converged before it reached the iteration a new iterate is taken from leaves the old
+        // one in place: it was a good start for this QP and the next one is closer still (SCP is converging)
+        snap_valid = res.snap_saved || (ctl.warm && res.status == 0 && snap_valid);
         ipm_total += res.iters;
         if (res.status & SCPB200_ST_QP_MAXITER) st |= SCPB200_ST_QP_MAXITER;
         if (res.status & SCPB200_ST_QP_PIVOT) st |= SCPB200_ST_QP_PIVOT;

@@ -459,9 +459,31 @@ static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B
     return 0;
 }
 
+static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
+
+// Launch shape.  A 128-thread CTA runs an interior-point iteration only ~7 % slower than a 256-thread one (the
+// iteration is a chain of short dependent phases), and three of them fit an SM where the register file holds two
+// 256-thread CTAs.  Measured on B200 (profiles/r01_sweep_shapes_b8192.txt, _b1024.txt): batches that keep every CTA busy for the whole
+// step gain 23 % from 3 x 128; a batch whose step ends on the longest chain of QPs of one instance (1024 instances per
+// GPU) is faster with 2 x 256.  SCPB200_THREADS overrides.
+#define SCP_THROUGHPUT_BATCH 2048
 static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
 {
-    pl->threads = env_int("SCPB200_THREADS", 256);
+    const int forced = env_int("SCPB200_THREADS", 0);
+    if (forced > 0) return plan_scp_threads(d, forced, pl);
+    int rc = plan_scp_threads(d, 256, pl);
+    if (rc || d->B < SCP_THROUGHPUT_BATCH) return rc;
+    SolvePlan narrow = *pl;
+    rc = plan_scp_threads(d, 128, &narrow);
+    if (rc) return rc;
+    if (narrow.all_shared && narrow.grid > pl->grid) *pl = narrow;
+    else rc = plan_scp_threads(d, 256, pl);            // restore the function attributes of the chosen shape
+    return rc;
+}
+
+static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
+{
+    pl->threads = threads;
     const int nVeh = d->nVeh, Hp = d->Hp, nObst = d->nObst;
     // pair blocks of the normal matrix on the tensor path while the horizon fits its accumulators
     int slots = Hp <= 8 * SCP_PAIR_NA ? 1 : 0;
