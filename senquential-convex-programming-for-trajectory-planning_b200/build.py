@@ -1,4 +1,8 @@
-"""Build libscpb200.so in-tree with nvcc for sm_100a (the only target)."""
+"""Build libscpb200.so in-tree with nvcc for sm_100a (the only target).
+
+The library is four translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
+dimensions (scp_solve_generic.cu) and with the literal dimensions of BASELINE.json's headline shape at two CTA widths
+(scp_solve_fixed.cu, compiled twice) — compiled in parallel and linked into one shared object."""
 from __future__ import annotations
 
 import os
@@ -8,33 +12,56 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscpb200.so")
-SOURCES = ["scpb200.cu"]
-DEPS = ["scp_common.cuh", "ipm_core.cuh", "ops_pair.cuh", "ops_dense.cuh", "scp_kernels.cuh", "scpb200.cu",
-        os.path.join("..", "..", "include", "scpb200.h")]
+OBJ = os.path.join(HERE, "build")
+# (object name, source, extra flags)
+UNITS = [("scpb200.o", "scpb200.cu", []),
+         ("scp_solve_generic.o", "scp_solve_generic.cu", []),
+         ("scp_solve_fixed_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_NT=256"]),
+         ("scp_solve_fixed_128.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_NT=128"])]
+DEPS = ["scp_common.cuh", "ipm_core.cuh", "ops_pair.cuh", "ops_dense.cuh", "scp_kernels.cuh", "scp_solve_kernel.cuh",
+        "scpb200.cu", "scp_solve_generic.cu", "scp_solve_fixed.cu", os.path.join("..", "..", "include", "scpb200.h")]
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-shared", "--use_fast_math=false"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(OUT):
+def needs_build(out: str = OUT) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if force or needs_build():
-        flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        cmd = ["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-              [os.path.join(CSRC, s) for s in SOURCES]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """Compile (if stale) and return the path of the shared object.  `defines` (e.g. ["-DSCP_PHASE_TIMERS"]) with a
+    different `out` builds a tuning variant next to the product library."""
+    if not (force or needs_build(out)):
+        return out
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(OBJ, tag)
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for obj, src, extra in UNITS:
+        cmd = ["nvcc"] + NVCC_FLAGS + list(defines) + extra + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", os.path.join(objdir, obj), os.path.join(CSRC, src)]
+        procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    fail = []
+    for obj, pr in procs:
+        so, se = pr.communicate()
         if verbose:
-            sys.stderr.write(r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    return OUT
+            sys.stderr.write(f"---- {obj}\n{se}")
+        if pr.returncode != 0:
+            fail.append(f"{obj}:\n{so}{se}")
+    if fail:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(fail))
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + \
+          [os.path.join(objdir, obj) for obj, _, _ in UNITS]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a for a in sys.argv[1:] if a.endswith(".so")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else OUT, defines=defs))

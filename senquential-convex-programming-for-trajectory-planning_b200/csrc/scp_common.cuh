@@ -143,7 +143,7 @@ SCP_FN double cta_red_max(const Cta &cta, const double *red, int slot)
 // Tuning builds (-DSCP_PHASE_TIMERS) accumulate, per code region, the cycles thread 0 of every CTA spends between
 // consecutive marks (regions end at CTA barriers, so thread 0's clock is the CTA's).  Off in the product build.
 #if SCP_DEVICE_BUILD && defined(SCP_PHASE_TIMERS)
-__device__ unsigned long long g_scp_prof[32];
+static __device__ unsigned long long g_scp_prof[32];   // one copy per translation unit
 #define SCP_TIMER_DECL long long scp_t_last = clock64();
 #define SCP_TIMER(id)                                                                         \
     if (threadIdx.x == 0) {                                                                   \

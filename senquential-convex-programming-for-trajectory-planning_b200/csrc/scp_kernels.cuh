@@ -571,7 +571,11 @@ struct ScpBump {
     {
         nd = (nd + 1) & ~(size_t)1;      // keep 16-byte alignment
         if (all_shared || sh_off + nd <= sh_lim) {
+#ifdef __CUDA_ARCH__
+            double *p = sh + sh_off;             // never null on the device (a select here is paid at every use)
+#else
             double *p = sh ? sh + sh_off : 0;
+#endif
             sh_off += nd;
             last_shared = true;
             return p;

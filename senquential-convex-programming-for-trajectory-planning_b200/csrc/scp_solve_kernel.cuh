@@ -1,0 +1,148 @@
+// scp_solve_kernel.cuh — the persistent SCP kernel (K4) as a template over the residency of the working set and,
+// optionally, literal problem dimensions and CTA width.  The library instantiates it in separate translation units
+// (scp_solve_generic.cu: run-time dimensions; scp_solve_fixed.cu: the shapes BASELINE.json names, once per CTA
+// width) which nvcc compiles in parallel; each unit exports a ScpKernelEntry through which the host code in
+// scpb200.cu queries occupancy and launches, so no device symbol crosses a unit boundary.
+#pragma once
+#include "scp_kernels.cuh"
+
+#ifndef SCP_MIN_CTAS
+#define SCP_MIN_CTAS 2
+#endif
+
+// ---- work queue of the SCP kernel -------------------------------------------------------------------------------
+// The unit of scheduling is ONE QP (one SCP iteration of one instance), not one instance: instances need between 1 and
+// max_scp_iter QPs, so with instance-granular scheduling a 1024-instance step waits for stragglers that started late.
+// A bounded FIFO ring in the workspace holds the instances that still have work; a CTA pops one, runs `quantum` SCP
+// iterations, and either finishes it or parks it (u + five scalars) and pushes it back at the tail.  Every live
+// instance therefore advances round-robin and the CTAs stay busy until the last QP of the step.
+//   hdr[0] = head ticket, hdr[1] = tail ticket, hdr[2] = instances not yet finished; slots[cap], cap = power of two
+//   >= 2B, empty = -1.  Pop ticket h is served by push ticket h (FIFO); a popper whose ticket is never served leaves
+//   when hdr[2] reaches 0.
+struct WorkQueue {
+    int *hdr, *slots;
+    int cap;
+};
+
+// everything a launch of the kernel needs, passed by value
+struct ScpKernelArgs {
+    scpb200_dims d;
+    scpb200_params p;
+    ScpIO io;
+    WorkQueue q;
+    double *gws;
+    size_t gl_stride, sh_lim;
+    int alpha_slots, want_H;
+};
+
+// what a translation unit exports per kernel instantiation
+struct ScpKernelEntry {
+    // sets the dynamic shared-memory limit of the kernel and returns its resident CTAs per SM for this launch shape
+    int (*prepare)(int threads, size_t smem_bytes, int *ctas_per_sm);
+    int (*launch)(int grid, int threads, size_t smem_bytes, void *stream, const ScpKernelArgs *a);
+    // tuning builds (-DSCP_PHASE_TIMERS): read and clear this unit's per-region cycle counters; null otherwise
+    int (*read_timers)(unsigned long long *out32);
+};
+
+#if SCP_DEVICE_BUILD
+__device__ __forceinline__ void queue_push(const WorkQueue &q, int b)
+{
+    const int t = atomicAdd(q.hdr + 1, 1);
+    int *p = q.slots + (t & (q.cap - 1));
+    while (atomicCAS(p, -1, b) != -1) __nanosleep(64);
+}
+
+// called by thread 0; returns an instance index, or -1 when every instance has finished
+__device__ __forceinline__ int queue_pop(const WorkQueue &q)
+{
+    const int h = atomicAdd(q.hdr, 1);
+    int *p = q.slots + (h & (q.cap - 1));
+    unsigned ns = 32;
+    for (;;) {
+        const int v = atomicExch(p, -1);
+        if (v >= 0) return v;
+        if (*(volatile int *)(q.hdr + 2) <= 0) return -1;
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+    }
+}
+
+// NVEH / HP / NT > 0: literal dimensions and CTA width.  After inlining the compiler folds every index computation
+// (n, n1, tile counts, divisions by Hp, strided loops over the CTA) into constants and unrolls the short loops; in
+// its generic form the kernel executes ~20 instructions of addressing and loop control per FP64 operation.
+template <bool ALL_SHARED, int NVEH, int HP, int NT>
+__global__ void __launch_bounds__(NT > 0 ? NT : SCP_MAX_THREADS, (NT > 0 && NT <= 128) ? 3 : SCP_MIN_CTAS)
+k_scp_solve(const __grid_constant__ ScpKernelArgs a)
+{
+    extern __shared__ double sh[];
+    __shared__ int slot;
+    scpb200_dims d = a.d;
+    if (NVEH > 0) { d.nVeh = NVEH; d.Hp = HP; d.nObst = 0; }
+    const int alpha_slots = NVEH > 0 ? 1 : a.alpha_slots, want_H = NVEH > 0 ? 0 : a.want_H;
+    Cta cta = {NT > 0 ? NT : (int)blockDim.x};
+    ScpBump bp = scp_bump(sh, a.sh_lim, ALL_SHARED ? (double *)0 : a.gws + (size_t)blockIdx.x * a.gl_stride, ALL_SHARED);
+    ScpMem s;
+    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const int b = queue_pop(a.q);
+            __threadfence();                       // acquire: the parked state written by the CTA that pushed b
+            slot = b;
+        }
+        __syncthreads();
+        const int b = slot;
+        if (b < 0) break;
+        const bool done = scp_solve_instance(cta, d, a.p, b, a.io, s);
+        __threadfence();                           // release: every thread's writes of this invocation ...
+        __syncthreads();                           // ... are ordered before thread 0 hands the instance on
+        if (threadIdx.x == 0) {
+            if (done) atomicSub(a.q.hdr + 2, 1);
+            else queue_push(a.q, b);
+        }
+    }
+}
+
+#ifdef SCP_PHASE_TIMERS
+#define SCP_ENTRY_TIMERS(NAME)                                                                         \
+    static int NAME##_read_timers(unsigned long long *out32)                                           \
+    {                                                                                                  \
+        if (cudaDeviceSynchronize() != cudaSuccess) return -1;                                         \
+        if (cudaMemcpyFromSymbol(out32, g_scp_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1; \
+        unsigned long long z[32] = {0};                                                                \
+        return cudaMemcpyToSymbol(g_scp_prof, z, sizeof z) == cudaSuccess ? 0 : -1;                    \
+    }
+#define SCP_ENTRY_TIMERS_PTR(NAME) NAME##_read_timers
+#else
+#define SCP_ENTRY_TIMERS(NAME)
+#define SCP_ENTRY_TIMERS_PTR(NAME) 0
+#endif
+
+// Defines `extern "C" const ScpKernelEntry *NAME(void)` for one instantiation of the kernel.
+#define SCP_DEFINE_KERNEL_ENTRY(NAME, ...)                                                             \
+    static int NAME##_prepare(int threads, size_t smem_bytes, int *ctas_per_sm)                        \
+    {                                                                                                  \
+        if (cudaFuncSetAttribute(k_scp_solve<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem_bytes) != cudaSuccess) return -1;                           \
+        if (cudaFuncSetAttribute(k_scp_solve<__VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                 cudaSharedmemCarveoutMaxShared) != cudaSuccess) return -1;            \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_scp_solve<__VA_ARGS__>, threads, \
+                                                             smem_bytes) == cudaSuccess ? 0 : -1;      \
+    }                                                                                                  \
+    static int NAME##_launch(int grid, int threads, size_t smem_bytes, void *stream, const ScpKernelArgs *a) \
+    {                                                                                                  \
+        k_scp_solve<__VA_ARGS__><<<grid, threads, smem_bytes, (cudaStream_t)stream>>>(*a);             \
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;                                             \
+    }                                                                                                  \
+    SCP_ENTRY_TIMERS(NAME)                                                                             \
+    extern "C" const ScpKernelEntry *NAME(void)                                                        \
+    {                                                                                                  \
+        static const ScpKernelEntry e = {NAME##_prepare, NAME##_launch, SCP_ENTRY_TIMERS_PTR(NAME)};   \
+        return &e;                                                                                     \
+    }
+#endif   // SCP_DEVICE_BUILD
+
+// entries of the library (defined in scp_solve_generic.cu / scp_solve_fixed.cu)
+extern "C" const ScpKernelEntry *scp_entry_generic_shared(void);
+extern "C" const ScpKernelEntry *scp_entry_generic_global(void);
+extern "C" const ScpKernelEntry *scp_entry_v8h10_t256(void);       // BASELINE.json configs[1]: 8 vehicles, Hp = 10
+extern "C" const ScpKernelEntry *scp_entry_v8h10_t128(void);

@@ -6,7 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "scp_kernels.cuh"
+#include "scp_solve_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -211,10 +211,6 @@ __global__ void __launch_bounds__(128) k_advance_linear(scpb200_dims d, const do
     }
 }
 
-#ifndef SCP_MIN_CTAS
-#define SCP_MIN_CTAS 2
-#endif
-
 // Persistent CTAs pull instance indices from a global counter (SCP/IPM iteration counts vary per instance).
 __device__ __forceinline__ int next_instance(int *counter, int *slot)
 {
@@ -222,42 +218,6 @@ __device__ __forceinline__ int next_instance(int *counter, int *slot)
     if (threadIdx.x == 0) *slot = atomicAdd(counter, 1);
     __syncthreads();
     return *slot;
-}
-
-// ---- work queue of the SCP kernel -------------------------------------------------------------------------------
-// The unit of scheduling is ONE QP (one SCP iteration of one instance), not one instance: instances need between 1 and
-// max_scp_iter QPs, so with instance-granular scheduling a 1024-instance step waits for stragglers that started late.
-// A bounded FIFO ring in the workspace holds the instances that still have work; a CTA pops one, runs `quantum` SCP
-// iterations, and either finishes it or parks it (u + five scalars) and pushes it back at the tail.  Every live
-// instance therefore advances round-robin and the CTAs stay busy until the last QP of the step.
-//   hdr[0] = head ticket, hdr[1] = tail ticket, hdr[2] = instances not yet finished; slots[cap], cap = power of two
-//   >= 2B, empty = -1.  Pop ticket h is served by push ticket h (FIFO); a popper whose ticket is never served leaves
-//   when hdr[2] reaches 0.
-struct WorkQueue {
-    int *hdr, *slots;
-    int cap;
-};
-
-__device__ __forceinline__ void queue_push(const WorkQueue &q, int b)
-{
-    const int t = atomicAdd(q.hdr + 1, 1);
-    int *p = q.slots + (t & (q.cap - 1));
-    while (atomicCAS(p, -1, b) != -1) __nanosleep(64);
-}
-
-// called by thread 0; returns an instance index, or -1 when every instance has finished
-__device__ __forceinline__ int queue_pop(const WorkQueue &q)
-{
-    const int h = atomicAdd(q.hdr, 1);
-    int *p = q.slots + (h & (q.cap - 1));
-    unsigned ns = 32;
-    for (;;) {
-        const int v = atomicExch(p, -1);
-        if (v >= 0) return v;
-        if (*(volatile int *)(q.hdr + 2) <= 0) return -1;
-        __nanosleep(ns);
-        if (ns < 1024) ns <<= 1;
-    }
 }
 
 // `order` (optional) lists the instances by descending expected work.  The first `npinned` of them are the likely
@@ -274,59 +234,6 @@ __global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_
         if (!keep_snap) state[(size_t)b * SCP_STATE_W + 6] = 0.0;    // no warm-start iterate from an earlier call
     }
     if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
-}
-
-// The body of k_scp_solve for given dimensions.  Called with run-time dims, and — for the shapes BASELINE.json names —
-// with literal dims, so that after inlining the compiler folds every index computation (n, n1, tile counts, divisions
-// by Hp) into constants and unrolls the short loops (the kernel executes ~20 instructions of addressing and loop
-// control per FP64 operation in its generic form).
-template <bool ALL_SHARED>
-__device__ __forceinline__ void scp_solve_body(const scpb200_dims &d, const scpb200_params &p, const ScpIO &io, const WorkQueue &q,
-                                               double *gws, size_t gl_stride, size_t sh_lim, int alpha_slots, int want_H,
-                                               double *sh, int *slot)
-{
-    Cta cta = {(int)blockDim.x};
-    ScpBump bp = scp_bump(sh, sh_lim, ALL_SHARED ? (double *)0 : gws + (size_t)blockIdx.x * gl_stride, ALL_SHARED);
-    ScpMem s;
-    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H);
-    for (;;) {
-        if (threadIdx.x == 0) {
-            const int b = queue_pop(q);
-            __threadfence();                       // acquire: the parked state written by the CTA that pushed b
-            *slot = b;
-        }
-        __syncthreads();
-        const int b = *slot;
-        if (b < 0) break;
-        const bool done = scp_solve_instance(cta, d, p, b, io, s);
-        __threadfence();                           // release: every thread's writes of this invocation ...
-        __syncthreads();                           // ... are ordered before thread 0 hands the instance on
-        if (threadIdx.x == 0) {
-            if (done) atomicSub(q.hdr + 2, 1);
-            else queue_push(q, b);
-        }
-    }
-}
-
-#ifndef SCP_SPECIALISE
-#define SCP_SPECIALISE 1
-#endif
-template <bool ALL_SHARED>
-__global__ void __launch_bounds__(SCP_MAX_THREADS, SCP_MIN_CTAS)
-k_scp_solve(scpb200_dims d, scpb200_params p, ScpIO io, WorkQueue q, double *gws, size_t gl_stride, size_t sh_lim,
-            int alpha_slots, int want_H)
-{
-    extern __shared__ double sh[];
-    __shared__ int slot;
-#if SCP_SPECIALISE
-    if (ALL_SHARED && d.nVeh == 8 && d.Hp == 10 && d.nObst == 0 && alpha_slots == 1 && want_H == 0) {
-        scpb200_dims dc = d;
-        dc.nVeh = 8; dc.Hp = 10; dc.nObst = 0;
-        scp_solve_body<ALL_SHARED>(dc, p, io, q, gws, gl_stride, sh_lim, 1, 0, sh, &slot);
-        return;
-    }
-#endif
-    scp_solve_body<ALL_SHARED>(d, p, io, q, gws, gl_stride, sh_lim, alpha_slots, want_H, sh, &slot);
 }
 
 // Pull order for the work queue: instances sorted by DEscending expected work (longest-processing-time-first), so
@@ -387,6 +294,7 @@ struct SolvePlan {
     int threads, grid, all_shared, alpha_slots, ctas_per_sm, want_H;
     size_t smem_bytes, sh_lim, gl_stride;    // sh_lim / gl_stride in doubles
     size_t ws_bytes;
+    const ScpKernelEntry *entry;             // K4: the instantiation this plan launches
 };
 
 #define WS_HEADER 256
@@ -412,6 +320,8 @@ static size_t snap_bytes(const scpb200_dims *d)
 }
 #define SCP_SM_SHARED_BYTES 233472      /* 228 KiB per SM on B200, 1 KiB reserved per resident CTA */
 
+// kshared / kglobal: int (*)(int threads, size_t smem_bytes, int *ctas_per_sm) — ScpKernelEntry::prepare of the kernel
+// that would be launched with the working set shared-resident / partly in the global workspace.
 // Pick the occupancy target: the largest number of CTAs per SM (<= max_ctas) for which the whole working set is
 // shared-resident; if it does not fit even alone, one CTA per SM with the tail of the set in the global workspace.
 template <class KS, class KG, class FP>
@@ -435,8 +345,7 @@ static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B
         pl->sh_lim = (size_t)1 << 40;
         pl->smem_bytes = shu * 8;
         pl->gl_stride = 0;
-        CUDA_TRY(cudaFuncSetAttribute(kshared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kshared, pl->threads, pl->smem_bytes));
+        if (kshared(pl->threads, pl->smem_bytes, &occ)) return set_err(SCPB200_ERR_CUDA, "kernel attribute / occupancy query failed");
     } else {
         size_t lim = (size_t)di.smem_optin / 8;
         if (force_global) lim = lim / 3;                       // testing aid: push the big arrays out
@@ -445,8 +354,7 @@ static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B
         pl->smem_bytes = shu * 8;
         pl->gl_stride = glu;
         pl->ctas_per_sm = 1;
-        CUDA_TRY(cudaFuncSetAttribute(kglobal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kglobal, pl->threads, pl->smem_bytes));
+        if (kglobal(pl->threads, pl->smem_bytes, &occ)) return set_err(SCPB200_ERR_CUDA, "kernel attribute / occupancy query failed");
     }
     if (occ < 1) return set_err(SCPB200_ERR_SIZE, "kernel cannot be resident (occupancy 0)");
     const int cap = env_int("SCPB200_CTAS_PER_SM", 0);
@@ -499,15 +407,22 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
         if (force_H >= 0 && want_H != force_H) continue;
         auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu); };
         SolvePlan cand = *pl;
-        int rc = plan_common(k_scp_solve<true>, k_scp_solve<false>, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand);
+        // the fixed-shape instantiations cover the layout without shared-resident cost blocks
+        const ScpKernelEntry *ks = scp_entry_generic_shared();
+        if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && Hp == 10 && nObst == 0 && slots == 1 && want_H == 0) {
+            if (threads == 256) ks = scp_entry_v8h10_t256();
+            else if (threads == 128) ks = scp_entry_v8h10_t128();
+        }
+        int rc = plan_common(ks->prepare, scp_entry_generic_global()->prepare, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand);
         if (rc) return rc;
         cand.want_H = want_H;
+        cand.entry = cand.all_shared ? ks : scp_entry_generic_global();
         if (!have || (cand.all_shared && (!best.all_shared || cand.ctas_per_sm > best.ctas_per_sm))) { best = cand; have = 1; }
     }
     *pl = best;
-    // plan_common leaves the function attribute of the last candidate: set it for the chosen one
-    if (pl->all_shared) CUDA_TRY(cudaFuncSetAttribute(k_scp_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-    else CUDA_TRY(cudaFuncSetAttribute(k_scp_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    // plan_common leaves the function attributes of the last candidate: set them for the chosen one
+    int occ = 0;
+    if (pl->entry->prepare(pl->threads, pl->smem_bytes, &occ)) return set_err(SCPB200_ERR_CUDA, "kernel attribute query failed");
     return 0;
 }
 
@@ -517,7 +432,16 @@ static int plan_qp(int n1, int mc, int B, SolvePlan *pl)
     pl->alpha_slots = 0;
     pl->want_H = 0;
     auto fp = [=](size_t lim, size_t *shu, size_t *glu) { ipm_footprint(n1, mc, lim, shu, glu); };
-    return plan_common(k_qp_dense<true>, k_qp_dense<false>, fp, 1, B, pl);
+    auto prep_shared = [](int threads, size_t smem, int *occ) -> int {
+        if (cudaFuncSetAttribute(k_qp_dense<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_qp_dense<true>, threads, smem) == cudaSuccess ? 0 : -1;
+    };
+    auto prep_global = [](int threads, size_t smem, int *occ) -> int {
+        if (cudaFuncSetAttribute(k_qp_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_qp_dense<false>, threads, smem) == cudaSuccess ? 0 : -1;
+    };
+    pl->entry = 0;
+    return plan_common(prep_shared, prep_global, fp, 1, B, pl);
 }
 
 extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
@@ -766,12 +690,13 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2),
                                                       p->qp_warm_start && p->qp_warm_carry, q, io.state);
     CUDA_TRY(cudaGetLastError());
-    if (pl.all_shared)
-        k_scp_solve<true><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, q, gws, pl.gl_stride, pl.sh_lim,
-                                                                     pl.alpha_slots, pl.want_H);
-    else
-        k_scp_solve<false><<<pl.grid, pl.threads, pl.smem_bytes, st>>>(*d, *p, io, q, gws, pl.gl_stride, pl.sh_lim,
-                                                                      pl.alpha_slots, pl.want_H);
+    ScpKernelArgs ka;
+    ka.d = *d; ka.p = *p; ka.io = io; ka.q = q; ka.gws = gws; ka.gl_stride = pl.gl_stride; ka.sh_lim = pl.sh_lim;
+    ka.alpha_slots = pl.alpha_slots; ka.want_H = pl.want_H;
+    if (pl.entry->launch(pl.grid, pl.threads, pl.smem_bytes, stream, &ka)) {
+        cudaGetLastError();
+        return set_err(SCPB200_ERR_CUDA, "k_scp_solve launch failed");
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -780,10 +705,14 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
 // tuning builds only: read (and clear) the per-region cycle counters
 extern "C" int scpb200_debug_read_timers(unsigned long long *out32)
 {
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpyFromSymbol(out32, g_scp_prof, sizeof(unsigned long long) * 32));
-    unsigned long long z[32] = {0};
-    CUDA_TRY(cudaMemcpyToSymbol(g_scp_prof, z, sizeof z));
+    const ScpKernelEntry *es[4] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
+                                   scp_entry_v8h10_t128()};
+    for (int i = 0; i < 32; ++i) out32[i] = 0;
+    for (int e = 0; e < 4; ++e) {
+        unsigned long long part[32];
+        if (!es[e]->read_timers || es[e]->read_timers(part)) return set_err(SCPB200_ERR_CUDA, "timer read failed");
+        for (int i = 0; i < 32; ++i) out32[i] += part[i];
+    }
     return 0;
 }
 #endif

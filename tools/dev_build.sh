@@ -1,5 +1,6 @@
 #!/bin/bash
-# Developer helper: rebuild the kernel-logic emulator, run its tests, rebuild libscpb200.so and the timers variant.
+# Developer helper: rebuild the kernel-logic emulator, run its tests, rebuild libscpb200.so and (with "timers") the
+# phase-timer variant.
 set -e
 cd /root/repo
 python -c "
@@ -8,6 +9,6 @@ from emu import emu
 emu.build(True)"
 timeout 3000 python -m pytest tests/test_kernel_logic_emu.py -x -q 2>&1 | tail -2
 P=/root/repo/senquential-convex-programming-for-trajectory-planning_b200
-python $P/build.py --force -v 2>&1 | grep -A2 "k_scp_solveILb1" | grep -E "registers|spill" || true
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DSCP_PHASE_TIMERS -o $P/libvariant_timers.so $P/csrc/scpb200.cu
+python $P/build.py --force -v 2>&1 | grep -A3 "k_scp_solveILb1ELi8" | grep -E "registers|spill" || true
+if [ "$1" = "timers" ]; then python $P/build.py --force -DSCP_PHASE_TIMERS $P/libvariant_timers.so; fi
 echo build-ok
