@@ -25,7 +25,8 @@
 //     double Op::row_dot(r)                     (A x)[r]
 //     double Op::col_dot(c)                     (A' w)[c]
 //     double Op::P_col(c, x)                    (P x)[c]
-//     void   Op::form_normal(cta, m, dd, dg)    S(lower) = P + A' diag(dd) A + diag(dg)      (dg[0..n1): box terms)
+//     void   Op::form_normal(cta, m, dd, dg, ddf, dgf)   S(lower) = P + A' diag(dd) A + diag(dg), with dd[r] = ddf(r) and
+//                                               dg[c] = dgf(c) (box terms) evaluated and stored by the operator
 // form_normal must leave the padding of S (rows >= n1) as unit diagonal / zero off-diagonal.
 #pragma once
 #include "scp_common.cuh"
@@ -196,6 +197,30 @@ SCP_FN void warp_tile_syrk(int lane, double *C, const double *A, const double *B
 #endif
 }
 
+// Two independent tiles at once: the loads of both are in flight before the first product issues (a single tile is a
+// dependent chain load -> DMMA -> DMMA -> store of ~250 cycles).
+SCP_FN void warp_tile_syrk2(int lane, double *C, const double *A, const double *B, double *C2, const double *A2, const double *B2)
+{
+#if SCP_DEVICE_BUILD
+    const int ia0 = scp_frag_rowmajor(lane, 0), ia1 = scp_frag_rowmajor(lane, 1), ic = scp_frag_c(lane);
+    double2 *cp = reinterpret_cast<double2 *>(C + ic), *cp2 = reinterpret_cast<double2 *>(C2 + ic);
+    const double a0 = A[ia0], a1 = A[ia1], b0 = B[ia0], b1 = B[ia1];
+    const double e0 = A2[ia0], e1 = A2[ia1], f0 = B2[ia0], f1 = B2[ia1];
+    double2 c = *cp, c2 = *cp2;
+    double n0 = 0.0, n1 = 0.0, m0 = 0.0, m1 = 0.0;
+    scp_dmma(n0, n1, a0, b0);
+    scp_dmma(m0, m1, e0, f0);
+    scp_dmma(n0, n1, a1, b1);
+    scp_dmma(m0, m1, e1, f1);
+    c.x -= n0; c.y -= n1; c2.x -= m0; c2.y -= m1;
+    *cp = c;
+    *cp2 = c2;
+#else
+    warp_tile_syrk(lane, C, A, B);
+    warp_tile_syrk(lane, C2, A2, B2);
+#endif
+}
+
 // out = sign * sum_{j < nprod} A_j B_j   with A_j = Abase + j*astride, B_j = Bbase + j*bstride (plain products)
 SCP_FN void warp_tile_gemm_sum(int lane, double *out, const double *Abase, int astride, const double *Bbase, int bstride,
                                int nprod, double sign)
@@ -290,11 +315,19 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
                 if (w > 0 || nw == 1) {
                     // tiles 1 .. ntile-1 over warps 1 .. nw-1 (a single-warp CTA does them itself), (ii, jj) advanced incrementally
                     const int nwork = nw > 1 ? nw - 1 : 1;
-                    int ii = 0, jj = nw > 1 ? w : 1;
-                    for (int t = jj; t < ntile; t += nwork, jj += nwork) {
-                        while (jj > ii) { jj -= ii + 1; ++ii; }
-                        warp_tile_syrk(lane, S + scp_tile_off(K + 1 + ii, K + 1 + jj), S + scp_tile_off(K + 1 + ii, K),
-                                       S + scp_tile_off(K + 1 + jj, K));
+                    const double *Lk = S + scp_tile_off(K + 1, K);               // panel tile of row K+1+ii: + ii(ii+2K+3)/2 tiles
+                    for (int t = nw > 1 ? w : 1; t < ntile; t += 2 * nwork) {
+                        int ii, jj, i2, j2;
+                        scp_tri_lookup(t, &ii, &jj);
+                        double *C1 = S + scp_tile_off(K + 1 + ii, K + 1 + jj);
+                        const double *A1 = Lk + (ii * (ii + 2 * K + 3) >> 1) * SCP_TILE2, *B1 = Lk + (jj * (jj + 2 * K + 3) >> 1) * SCP_TILE2;
+                        if (t + nwork < ntile) {                                   // warp-uniform
+                            scp_tri_lookup(t + nwork, &i2, &j2);
+                            warp_tile_syrk2(lane, C1, A1, B1, S + scp_tile_off(K + 1 + i2, K + 1 + j2),
+                                            Lk + (i2 * (i2 + 2 * K + 3) >> 1) * SCP_TILE2, Lk + (j2 * (j2 + 2 * K + 3) >> 1) * SCP_TILE2);
+                        } else {
+                            warp_tile_syrk(lane, C1, A1, B1);
+                        }
                     }
                 }
             WARP_PHASE_END
@@ -446,17 +479,10 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         ipm_snapshot(cta, m, ctl.snap, false);
     } else {
         // ---- starting point (coneqp): (P + G'G) x = G'h - q ; z = Gx - h ; s = -z ; shift ------------
-        CTA_PHASE(tid)
-            for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = 1.0;            // dd = 1
-            for (int c = tid; c < n1p; c += cta.nt) {
-                double d = 0.0;
-                if (ipm_has_ub(m, ctl, c)) d += 1.0;
-                if (ipm_has_lb(m, ctl, c)) d += 1.0;
-                m.tn[c] = d;                                                   // box part of the diagonal
-            }
-        CTA_PHASE_END
         SCP_TIMER(0)
-        op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
+        op.form_normal(cta, m, m.dsA, m.tn, [](int) { return 1.0; },                         // dd = 1
+                       [&](int c) { return (ipm_has_ub(m, ctl, c) ? 1.0 : 0.0) + (ipm_has_lb(m, ctl, c) ? 1.0 : 0.0); }
+                       SCP_TIMER_PASS);
         op.prep(cta, (const double *)0, m.bA);
         CTA_PHASE(tid)
             for (int c = tid; c < n1; c += cta.nt) {
@@ -573,16 +599,13 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         SCP_TIMER(9)
 
         // ---- normal matrix with dd = z e and its inverted factor -----------------------------------
-        CTA_PHASE(tid)
-            for (int r = tid; r < mc; r += cta.nt) m.dsA[r] = m.zA[r] * m.eA[r];          // dd in dsA
-            for (int c = tid; c < n1p; c += cta.nt) {
-                double d = 0.0;
-                if (ipm_has_ub(m, ctl, c)) d += m.zU[c] * m.eU[c];
-                if (ipm_has_lb(m, ctl, c)) d += m.zL[c] * m.eL[c];
-                m.tn[c] = d;
-            }
-        CTA_PHASE_END
-        op.form_normal(cta, m, m.dsA, m.tn SCP_TIMER_PASS);
+        op.form_normal(cta, m, m.dsA, m.tn, [&](int r) { return m.zA[r] * m.eA[r]; },            // dd (kept in dsA)
+                       [&](int c) {
+                           double d = 0.0;
+                           if (ipm_has_ub(m, ctl, c)) d += m.zU[c] * m.eU[c];
+                           if (ipm_has_lb(m, ctl, c)) d += m.zL[c] * m.eL[c];
+                           return d;
+                       } SCP_TIMER_PASS);
         SCP_TIMER(1)
         chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
 

@@ -39,12 +39,14 @@ struct DenseOp {
     }
 
     // S(lower) = P + A' diag(dd) A + diag(dg): clear, then accumulate
-    template <class Mem>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg SCP_TIMER_ARG)
+    template <class Mem, class DD, class DG>
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, DD ddf, DG dgf SCP_TIMER_ARG)
     {
         CTA_PHASE(tid)
             const int tot = (m.T * (m.T + 1) >> 1) * SCP_TILE2;
             for (int e = tid; e < tot; e += cta.nt) m.S[e] = 0.0;
+            for (int r = tid; r < mc; r += cta.nt) dd[r] = ddf(r);
+            for (int c = tid; c < m.n1p; c += cta.nt) dg[c] = dgf(c);
         CTA_PHASE_END
         CTA_PHASE(tid)
             for (int c = tid; c < m.n1p; c += cta.nt) m.S[scp_sidx(c, c)] = c < n1 ? dg[c] : 1.0;

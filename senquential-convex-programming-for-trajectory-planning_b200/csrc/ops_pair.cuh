@@ -23,6 +23,7 @@ struct PairOp {
     double xom, wsum;     // omega component of x / sum of w of the last prep
     double *red;          // reduction scratch
     double *Msm;          // [n][3] scratch: per (vehicle, step) sum of 4 dd dbar dbar' (xx, xy, yy)
+    const int *rowtab;    // [mc] (i*Hp + k) | (j*Hp + k) << 16 per row (shared; built once per instance)
     int alpha_slots;      // pair-block mode: > 0 tensor path (pair_block_mma, Hp <= 64), 0 entry by entry
 
     SCP_MFN int pair_index(int i, int j) const { return i * nVeh - (i * (i + 1) >> 1) + (j - i - 1); }
@@ -91,17 +92,14 @@ struct PairOp {
     SCP_MFN double row_dot(int r) const
     {
         double dx, dy;
+        const int t = rowtab[r], ci = t & 0xffff;
         if (r < mcv) {
-            const int p = r / Hp, k = r - p * Hp;
-            int i = 0, rem = p;
-            while (rem >= nVeh - 1 - i) { rem -= nVeh - 1 - i; ++i; }
-            const int j = i + 1 + rem;
-            dx = resp[(i * Hp + k) * 2] - resp[(j * Hp + k) * 2];
-            dy = resp[(i * Hp + k) * 2 + 1] - resp[(j * Hp + k) * 2 + 1];
+            const int cj = t >> 16;
+            dx = resp[ci * 2] - resp[cj * 2];
+            dy = resp[ci * 2 + 1] - resp[cj * 2 + 1];
         } else {
-            const int q = r - mcv, v = q / (nObst * Hp), k = q % Hp;
-            dx = resp[(v * Hp + k) * 2];
-            dy = resp[(v * Hp + k) * 2 + 1];
+            dx = resp[ci * 2];
+            dy = resp[ci * 2 + 1];
         }
         return -2.0 * (dbar[r * 2] * dx + dbar[r * 2 + 1] * dy) - xom;
     }
@@ -205,27 +203,40 @@ struct PairOp {
     //   omega row         S[n][(v,a)] = -(A'dd)[(v,a)],  S[n][n] = sum dd + dg[n]
     //   pair blocks (j>i) S[(j,b),(i,a)] = -sum_{k>=max(a,b)} aj[k][b] ai[k][a],  ai = 2 dd_r dbar_r.g_i[k-a],
     //                     aj = 2 dbar_r.g_j[k-b]: one warp per block on the tensor path (pair_block_mma).
-    template <class Mem>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, const double *dd, const double *dg SCP_TIMER_ARG)
+    // Two phases: (1) per (vehicle, step): forces of dd (for the omega row), M_v(k), sum dd, padding; (2) every entry of S
+    // — the pair blocks by warps, then omega row and diagonal blocks by threads, without a barrier in between (they
+    // read the same inputs and write disjoint entries).
+    // The scalings come as functions (ddf(r): row scaling, dgf(c): box term of the diagonal) evaluated inside phase 1 —
+    // no separate pass over the rows; dd[r] and dg[c] are stored for phase 2.
+    template <class Mem, class DD, class DG>
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, DD ddf, DG dgf SCP_TIMER_ARG)
     {
         double *S = m.S;
-        const double sd = forces(cta, dd);            // frc = A'dd in force form (for the omega row)
-        SCP_TIMER(12)
+        CTA_RED_BEGIN(cta, 1)
         CTA_PHASE(tid)
-            for (int c = tid; c < n; c += cta.nt) {   // M_v(k)
+            double sw = 0.0;
+            for (int c = tid; c < m.n1p; c += cta.nt) dg[c] = dgf(c);
+            for (int c = tid; c < n; c += cta.nt) {
                 const int v = c / Hp, k = c - v * Hp;
-                double mxx = 0.0, mxy = 0.0, myy = 0.0;
+                double fx = 0.0, fy = 0.0, mxx = 0.0, mxy = 0.0, myy = 0.0;
                 for (int o = 0; o < nVeh; ++o) {
                     if (o == v) continue;
                     const int r = (v < o ? pair_index(v, o) : pair_index(o, v)) * Hp + k;
-                    const double w4 = 4.0 * dd[r], dx = dbar[r * 2], dy = dbar[r * 2 + 1];
-                    mxx += w4 * dx * dx; mxy += w4 * dx * dy; myy += w4 * dy * dy;
+                    const double d = ddf(r);
+                    const double w2 = 2.0 * d, dx = dbar[r * 2], dy = dbar[r * 2 + 1];
+                    const double wx = w2 * dx, wy = w2 * dy;
+                    if (v < o) { fx -= wx; fy -= wy; dd[r] = d; sw += d; } else { fx += wx; fy += wy; }
+                    mxx += 2.0 * wx * dx; mxy += 2.0 * wx * dy; myy += 2.0 * wy * dy;
                 }
                 for (int o = 0; o < nObst; ++o) {
                     const int r = mcv + (v * nObst + o) * Hp + k;
-                    const double w4 = 4.0 * dd[r], dx = dbar[r * 2], dy = dbar[r * 2 + 1];
-                    mxx += w4 * dx * dx; mxy += w4 * dx * dy; myy += w4 * dy * dy;
+                    const double d = ddf(r);
+                    const double w2 = 2.0 * d, dx = dbar[r * 2], dy = dbar[r * 2 + 1];
+                    const double wx = w2 * dx, wy = w2 * dy;
+                    fx -= wx; fy -= wy; dd[r] = d; sw += d;
+                    mxx += 2.0 * wx * dx; mxy += 2.0 * wx * dy; myy += 2.0 * wy * dy;
                 }
+                frc[c * 2] = fx; frc[c * 2 + 1] = fy;
                 Msm[c * 3] = mxx; Msm[c * 3 + 1] = mxy; Msm[c * 3 + 2] = myy;
             }
             // padding rows/columns of S: zero off-diagonal, unit diagonal (the factorisation keeps them so)
@@ -233,8 +244,25 @@ struct PairOp {
                 for (int j = 0; j < c; ++j) S[scp_sidx(c, j)] = 0.0;
                 S[scp_sidx(c, c)] = 1.0;
             }
-        CTA_PHASE_END
+            CTA_RED_SUM(cta, red, 0, tid, sw)
+        CTA_PHASE_END_RED(cta, red, 1)
+        const double sd = cta_red_sum(cta, red, 0);
+        wsum = sd;
         SCP_TIMER(13)
+        if (alpha_slots > 0) {
+            const int npair = nVeh * (nVeh - 1) >> 1;
+            WARP_SECTION(w, nw)
+                WARP_PHASE(lane)
+                    // pairs dealt out from the last warp down: the first warps carry one pair fewer and more of the
+                    // entry-by-entry work below
+                    for (int p = nw - 1 - w; p < npair; p += nw) {
+                        int i = 0, q = p;
+                        while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
+                        pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
+                    }
+                WARP_PHASE_END
+            WARP_SECTION_END
+        }
         CTA_PHASE(tid)
             // omega row
             for (int c = tid; c < n; c += cta.nt) {
@@ -279,18 +307,5 @@ struct PairOp {
             }
         CTA_PHASE_END
         SCP_TIMER(14)
-        if (alpha_slots > 0) {
-            const int npair = nVeh * (nVeh - 1) >> 1;
-            WARP_SECTION(w, nw)
-                WARP_PHASE(lane)
-                    for (int p = w; p < npair; p += nw) {
-                        int i = 0, q = p;
-                        while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
-                        pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
-                    }
-                WARP_PHASE_END
-            WARP_SECTION_END
-            CTA_SYNC
-        }
     }
 };

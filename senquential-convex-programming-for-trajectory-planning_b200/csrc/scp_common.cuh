@@ -185,6 +185,30 @@ SCP_HDFN int scp_sidx(int ci, int cj)
     return scp_tile_off(ci >> 3, cj >> 3) + scp_tphys(ci & 7, cj & 7);
 }
 // t -> (ii, jj) with ii >= jj, t = ii(ii+1)/2 + jj
+SCP_HDFN void scp_tri_decode(int t, int *ii, int *jj);
+// The same through a table for the tile loops of the factorisation, whose t is warp-uniform (constant-cache broadcast,
+// two loads instead of a search).
+#define SCP_TRI_TAB_ROWS 52
+#define SCP_TRI_TAB (SCP_TRI_TAB_ROWS * (SCP_TRI_TAB_ROWS + 1) / 2)
+struct ScpTriTab {
+    unsigned char ii[SCP_TRI_TAB], jj[SCP_TRI_TAB];
+    constexpr ScpTriTab() : ii(), jj()
+    {
+        int t = 0;
+        for (int i = 0; i < SCP_TRI_TAB_ROWS; ++i)
+            for (int j = 0; j <= i; ++j) { ii[t] = (unsigned char)i; jj[t] = (unsigned char)j; ++t; }
+    }
+};
+#if SCP_DEVICE_BUILD
+static __constant__ ScpTriTab c_scp_tri = ScpTriTab();
+#else
+static const ScpTriTab c_scp_tri = ScpTriTab();
+#endif
+SCP_FN void scp_tri_lookup(int t, int *ii, int *jj)
+{
+    if (t < SCP_TRI_TAB) { *ii = c_scp_tri.ii[t]; *jj = c_scp_tri.jj[t]; }
+    else scp_tri_decode(t, ii, jj);
+}
 SCP_HDFN void scp_tri_decode(int t, int *ii, int *jj)
 {
     int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);      // estimate, corrected below

@@ -611,7 +611,11 @@ SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc)
     {
         const size_t rows = (size_t)((mc + 1) & ~1);          // dsA, dzA, ccA back to back (see ipm_carve_big)
         double *blk = bp.take(3 * rows);
+#ifdef __CUDA_ARCH__
+        m.dsA = blk; m.dzA = blk + rows; m.ccA = blk + 2 * rows;
+#else
         m.dsA = blk; m.dzA = blk ? blk + rows : 0; m.ccA = blk ? blk + 2 * rows : 0;
+#endif
     }
     m.eA = bp.take(mc);
 }
@@ -631,6 +635,7 @@ SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 struct ScpMem {
     IpmMem ipm;
     double *g, *dbar, *resp, *frc, *ucur, *Msm, *Hs;
+    int *rowtab;       // [mc] per constraint row: (i*Hp + k) | (j*Hp + k) << 16  (obstacle rows: vehicle index only)
     int alpha_slots;
     bool H_local;      // Hs is shared-resident: the instance's cost blocks are copied there once per instance
 };
@@ -646,6 +651,7 @@ SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int
     s.dbar = bp.take((size_t)mc * 2);
     s.resp = bp.take((size_t)n * 2);
     s.frc = bp.take((size_t)n * 2);
+    s.rowtab = (int *)bp.take((size_t)(mc + 1) / 2);
     // ucur (the SCP iterate) is dead while the interior-point method runs and rx is dead outside it: one array.
     s.ucur = s.ipm.rx;
     // Msm (per (vehicle, step) 2x2 aggregates) is only live inside form_normal, where ccA is dead.
@@ -721,7 +727,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
     op.g = s.g; op.H = s.H_local ? s.Hs : HB; op.dbar = s.dbar; op.resp = s.resp; op.frc = s.frc; op.red = m.red;
     op.xom = 0.0; op.wsum = 0.0;
-    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots;
+    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots; op.rowtab = s.rowtab;
 
     double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
     const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance
@@ -730,6 +736,11 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
     CTA_PHASE(tid)
         for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = gB[e];
+        for (int r = tid; r < mc; r += cta.nt) {
+            int i, j, o, k;
+            scp_row_decode(nVeh, Hp, nObst, mcv, r, &i, &j, &o, &k);
+            s.rowtab[r] = (i * Hp + k) | ((j >= 0 ? j * Hp + k : 0xffff) << 16);
+        }
         if (s.H_local)
             for (int e = tid; e < n * Hp; e += cta.nt) s.Hs[e] = HB[e];
         for (int c = tid; c < m.n1p; c += cta.nt) {
