@@ -226,15 +226,27 @@ SCP_FN void warp_tile_gemm_sum(int lane, double *out, const double *Abase, int a
                                int nprod, double sign)
 {
 #if SCP_DEVICE_BUILD
-    double n0 = 0.0, n1 = 0.0;
+    // two accumulator pairs (even / odd products): the DMMA chain of one tile would otherwise be 2 * nprod deep
+    double n0 = 0.0, n1 = 0.0, m0 = 0.0, m1 = 0.0;
     const int ia0 = scp_frag_rowmajor(lane, 0), ia1 = scp_frag_rowmajor(lane, 1);
     const int ib0 = scp_frag_colmajor(lane, 0), ib1 = scp_frag_colmajor(lane, 1);
-    for (int j = 0; j < nprod; ++j) {
+    int j = 0;
+    for (; j + 1 < nprod; j += 2) {
+        const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
+        const double a0 = A[ia0], a1 = A[ia1], b0 = B[ib0], b1 = B[ib1];
+        const double e0 = A[astride + ia0], e1 = A[astride + ia1], f0 = B[bstride + ib0], f1 = B[bstride + ib1];
+        scp_dmma(n0, n1, a0, b0);
+        scp_dmma(m0, m1, e0, f0);
+        scp_dmma(n0, n1, a1, b1);
+        scp_dmma(m0, m1, e1, f1);
+    }
+    if (j < nprod) {
         const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
         const double a0 = A[ia0], a1 = A[ia1], b0 = B[ib0], b1 = B[ib1];
         scp_dmma(n0, n1, a0, b0);
         scp_dmma(n0, n1, a1, b1);
     }
+    n0 += m0; n1 += m1;
     double2 c;
     c.x = sign * n0; c.y = sign * n1;
     *reinterpret_cast<double2 *>(out + scp_frag_c(lane)) = c;

@@ -371,10 +371,11 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
 
 // Launch shape.  A 128-thread CTA runs an interior-point iteration only ~7 % slower than a 256-thread one (the
 // iteration is a chain of short dependent phases), and three of them fit an SM where the register file holds two
-// 256-thread CTAs.  Measured on B200 (profiles/r01_sweep_shapes_b8192.txt, _b1024.txt): batches that keep every CTA busy for the whole
-// step gain 23 % from 3 x 128; a batch whose step ends on the longest chain of QPs of one instance (1024 instances per
-// GPU) is faster with 2 x 256.  SCPB200_THREADS overrides.
-#define SCP_THROUGHPUT_BATCH 2048
+// 256-thread CTAs.  Measured on B200 (profiles/r01_sweep_shapes_*.txt, profiles/README.md): a batch that keeps every CTA
+// busy for the whole step gains 23-26 % from 3 x 128 (8192 instances), the 1024-instance benchmark 3 %; batches with
+// fewer than two instances per CTA end on the longest chain of QPs of one instance and keep 2 x 256.
+// SCPB200_THREADS overrides.
+#define SCP_THROUGHPUT_BATCH 888
 static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
 {
     const int forced = env_int("SCPB200_THREADS", 0);
