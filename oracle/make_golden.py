@@ -91,15 +91,24 @@ def circle_scenario(nveh, radius, Hp):
     return sc
 
 
-def run(nveh, radius, Hp, nsim):
+def frog_scenario(Hp):
+    """Scenarios.py:127-146: one vehicle crossing two lanes of moving obstacles (nVeh = 1, nObst = 22)."""
+    sc = Scenario(False)
+    sc.get_frog_scenario()
+    sc.Hp = sc.Hu = Hp
+    sc.uLim = sc.mechanicalSteeringLimit           # F1
+    return sc
+
+
+def run(nveh, radius, Hp, nsim, frog=False):
     ITER_INPUTS.clear()
     QP_ITERS.clear()
     cp_stub.CAPTURE.clear()
-    sc = circle_scenario(nveh, radius, Hp)
+    sc = frog_scenario(Hp) if frog else circle_scenario(nveh, radius, Hp)
     sim = ref_main.Simulation(sc, doOnlinePlot=False, isNoise=False)
     if nsim is not None:
         sim.scenario.Nsim = nsim
-    ref_main.scenario_choice = "Circle"
+    ref_main.scenario_choice = "Frog" if frog else "Circle"
     cwd = os.getcwd()
     tmp = tempfile.mkdtemp()
     os.makedirs(os.path.join(tmp, "Data"))
@@ -126,6 +135,7 @@ def scenario_constants(sc):
         Q=np.array(sc.Q, float), Q_final=np.array(sc.Q_final, float), R=np.array(sc.R, float),
         poly=np.array([np.asarray(r, float) for r in sc.referenceTrajectories]),
         x_init=np.array([np.asarray(x0).ravel() for x0 in sc.x0]), u_init=np.array(sc.u0, float),
+        nObst=sc.nObst, dsafeObstacles=np.array(sc.dsafeObstacles, float),
     )
 
 
@@ -165,12 +175,17 @@ def step_record(sim, i, dense_iters):
             rec[f"bineq_{it}"] = np.ravel(log["bineq"][it])
             rec[f"lb_{it}"] = np.ravel(log["lb"][it])
             rec[f"ub_{it}"] = np.ravel(log["ub"][it])
+    if sc.nObst:
+        # obstacle rows (SCP_controller.py:106-114): predicted obstacle positions in the kernels' [nObst, Hp, 2] layout
+        rec["obst"] = np.transpose(np.asarray(It.obstacleFutureTrajectories, float), (0, 2, 1)).copy()
     # a9 on the final u, straight from the reference
     ctl = ref_main.SCPcontroller(sc, It, [])
     with contextlib.redirect_stdout(io.StringIO()):
         feas, obj, _, _, mv, sv, civ, _ = ctl.QCQP_evaluate(out["u"].reshape(-1, 1))
     rec.update(eval_feasible=bool(feas), eval_obj=float(np.ravel(obj)[0]), eval_max_violation=float(mv),
                eval_sum_violations=float(sv), eval_ci=civ)
+    if sc.nObst:
+        rec["eval_cio"] = np.asarray(ctl.QCQP_evaluate(out["u"].reshape(-1, 1))[7], float)
     return rec
 
 
@@ -179,8 +194,8 @@ def patch_raw_controls(sim_cls):
     pass
 
 
-def collect(nveh, radius, Hp, nsim, steps, dense_iters, tag, full_run=False):
-    sim = run(nveh, radius, Hp, nsim)
+def collect(nveh, radius, Hp, nsim, steps, dense_iters, tag, full_run=False, frog=False):
+    sim = run(nveh, radius, Hp, nsim, frog=frog)
     sc = sim.scenario
     # raw (pre-clamp) U per step = forward_U of the stored 'u' (SCP_controller.py:69-70)
     sim.controlPredictions_raw = [o["u"].reshape(sc.nVeh, sc.Hp).T.copy() for o in sim.controllerOutputs]
@@ -241,6 +256,8 @@ def main():
         collect(8, 45, 20, 8, [5, 7], [0], "circle8_hp20")
     if args.only in (None, "hp50"):
         collect(8, 90, 50, 4, [3], [0], "circle8_hp50")
+    if args.only in (None, "frog"):
+        collect(1, 0, 10, 12, [5, 9], [0, -1], "frog1_hp10", frog=True)
     if args.only in (None, "small"):
         collect(3, 30, 10, 12, [8], [0, -1], "circle3_hp10")
 

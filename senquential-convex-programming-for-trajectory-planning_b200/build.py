@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscpb200.so")
-OBJ = os.path.join(HERE, "build")
+# object files are scratch: gpurun_out/ is neither tracked by git nor shipped to the GPU box (the linked .so is)
+OBJ = os.path.join(os.path.dirname(HERE), "gpurun_out", "build_obj")
 # (object name, source, extra flags)
 UNITS = [("scpb200.o", "scpb200.cu", []),
          ("scp_solve_generic.o", "scp_solve_generic.cu", []),

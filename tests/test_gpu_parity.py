@@ -16,7 +16,9 @@ from conftest import GOLDEN, golden_setup_inputs, load_golden
 pytestmark = pytest.mark.gpu
 
 PKG = "senquential-convex-programming-for-trajectory-planning_b200"
-STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+ALL_STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+STEP_FILES = [f for f in ALL_STEP_FILES if "frog" not in f]          # vehicle-pair rows only
+FROG_FILES = [f for f in ALL_STEP_FILES if "frog" in f]              # the reference's obstacle scenario (nVeh = 1, nObst = 22)
 NOT50 = [f for f in STEP_FILES if "hp50" not in f]
 
 
@@ -255,6 +257,50 @@ def test_obstacle_rows_vs_oracle(mods, oracle):
         assert np.abs(host(out[k])[1] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), k
 
 
+@pytest.mark.parametrize("fname", FROG_FILES)
+def test_frog_scenario_obstacle_rows_vs_reference(mods, fname):
+    """The reference's own obstacle scenario (Scenarios.py:127-146; rows SCP_controller.py:106-114, 321-326) on the GPU:
+    K2 against the dense QP the reference logged, K4 teacher-forced against its per-iteration solutions, and free-running
+    against its iteration count and result (obstacle_eval_mode = 1: the nesting of SCP_controller.py:249-263)."""
+    capi, batch, torch = mods["capi"], mods["batch"], mods["torch"]
+    G = load_golden(fname)
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    nVeh, Hp, nObst, nit = int(G["sc_nVeh"]), int(G["sc_Hp"]), int(G["sc_nObst"]), int(G["scp_iters"])
+
+    def frog_batch(B, **pkw):
+        p = capi.Params()
+        capi.load().scpb200_default_params(C.byref(p))
+        p.dt, p.uLim, p.dsafeExtra, p.obstacle_eval_mode = float(G["sc_dt"]), float(G["sc_uLim"]), float(G["sc_dsafeExtra"]), 1
+        for k, v in pkw.items():
+            setattr(p, k, v)
+        bs = batch.BatchSCP(B, nVeh, Hp, nObst=nObst, params=p)
+        rep = lambda a: np.repeat(a, B, axis=0)
+        bs.load_inputs(x0=rep(x0), u0=rep(u0), veh=rep(veh), poly=rep(poly), dsafe=rep(G["sc_dsafeVehicles"][None]),
+                       dsafe_obst=rep(G["sc_dsafeObstacles"][None]), obst=rep(G["obst"][None]))
+        return bs
+
+    bs = frog_batch(nit, max_scp_iter=1)
+    bs.load_inputs(u=G["prev_u"][:nit])
+    bs.controller_step()
+    u, log = host(bs.u), host(bs.log)
+    for it in range(nit):
+        assert np.abs(u[it] - G["x"][it][:-1]).max() < 1e-6, it
+        assert abs(log[it, 0, 1] - G["SCP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][it]))
+    D = {k: host(v) for k, v in bs.assemble_dense(torch.as_tensor(G["prev_u"][:nit]).cuda()).items()}
+    for it in sorted(int(k.split("_")[1]) for k in G if k.startswith("Aineq_")):
+        assert np.abs(D["P"][it] - G[f"P_{it}"]).max() <= 1e-12 * np.abs(G[f"P_{it}"]).max()
+        assert np.abs(D["A"][it] - G[f"Aineq_{it}"]).max() <= 1e-11 * np.abs(G[f"Aineq_{it}"]).max()
+        assert np.abs(D["b"][it] - G[f"bineq_{it}"]).max() <= 1e-11 * np.abs(G[f"bineq_{it}"]).max()
+        np.testing.assert_array_equal(D["lb"][it], G[f"lb_{it}"])
+        np.testing.assert_array_equal(D["ub"][it], G[f"ub_{it}"])
+    bs = frog_batch(1)
+    bs.load_inputs(u=G["u_warm"][None])
+    bs.controller_step()
+    assert int(host(bs.scp_iters)[0]) == nit
+    assert np.abs(host(bs.u)[0] - G["u_final"]).max() < 1e-6
+    assert np.abs(host(bs.traj)[0] - G["Traj"]).max() < 1e-4
+
+
 def test_closed_loop_rollout_against_reference_run(mods):
     """The reference's own 50-step closed loop (golden run): at every MPC step feed the reference's measured
     state (x0, u0) and warm start; controller outputs must match where the SCP map is stable, and the number of
@@ -424,6 +470,52 @@ def test_plant_step_and_device_resident_closed_loop(mods):
     assert dmin > 3.0                                                           # reference run: 3.0661 m
     goal = R["sc_poly"][:, 1, :]
     assert np.linalg.norm(pos[-1] - goal, axis=1).max() < np.linalg.norm(ref[-1, :, :2] - goal, axis=1).max() + 1.0
+
+
+def test_batch_rollout_in_the_reference_result_format(mods, tmp_path):
+    """a batched device-resident rollout recorded under the keys / shapes main.py:213-224 dumps, against
+    the reference's own run up to its first symmetric conflict (MPC step 6), and read back the way draw_video.py does."""
+    import importlib
+    results = importlib.import_module(PKG + ".results")
+    R = load_golden("circle8_hp10_run.npz")
+    G0 = load_golden("circle8_hp10_step0.npz")
+    B, Nsim, nref = 2, 9, 6
+    bs = make_batch(mods, G0, B=B)
+    ro = results.BatchRollout(bs, np.repeat(R["sc_x_init"][None], B, 0), np.repeat(R["sc_u_init"][None], B, 0),
+                              mech_limit=float(R["sc_mechanicalSteeringLimit"]), lat_acc_limit=float(R["sc_lateralAccelerationLimit"]),
+                              duLim=float(R["sc_duLim"]), delay_u=float(R["sc_delay_u"]), tick_length=float(R["sc_tick_length"]),
+                              Nsim=Nsim)
+    assert (ro.tps, ro.tdu, ro.ticks_total) == (int(R["sc_ticks_per_sim"]), int(R["sc_ticks_delay_u"]), Nsim * 40)
+    ro.run()
+    A, A1 = ro.result_arrays(0), ro.result_arrays(1)
+    for k in results.RESULT_KEYS[:9]:
+        np.testing.assert_array_equal(A[k], A1[k])                              # identical scenarios, identical records
+    nt = nref * ro.tps
+    assert np.abs(A["vehiclePathFullRes"][:, :, :nt + 1:10] - R["vehiclePath_every10"][:, :, :nt // 10 + 1]).max() < 1e-4
+    assert np.abs(A["controlPathFullRes"][:, :nt + 1:10] - R["controlPath_every10"][:, :nt // 10 + 1]).max() < 1e-6
+    assert np.abs(A["trajectoryPredictions"][..., :nref] - np.moveaxis(R["Traj"][:nref], 0, -1)).max() < 1e-4
+    assert np.abs(A["controlPredictions"][..., :nref] - np.moveaxis(R["U_clamped"][:nref], 0, -1)).max() < 1e-5
+    assert np.abs(A["ReferenceTrajectory"][..., :nref] - np.moveaxis(R["RefPts"][:nref], 0, -1)).max() < 1e-4
+    assert np.abs(A["initial_pos"][..., :nref] - np.moveaxis(R["x0"][:nref, :, :2], 0, -1).transpose(1, 0, 2)).max() < 1e-4
+    np.testing.assert_allclose(A["evaluations_obj_value"][:nref], R["evaluations_obj_value"][:nref], rtol=1e-5, atol=1e-9)
+    assert (ro.scp_iters[0, :nref] == R["scp_iters"][:nref]).all()
+    # the actuator path is piecewise constant: step i's first clamped command from tick (i+1)*40 + 4 on
+    cp = A["controlPathFullRes"]
+    for i in range(Nsim - 2):
+        seg = cp[:, (i + 1) * 40 + 4:(i + 2) * 40 + 4]
+        assert (seg == A["controlPredictions"][0, :, i][:, None]).all()
+    assert not np.isnan(A["vehiclePathFullRes"]).any() and np.isnan(cp).sum() == 0
+    # file round trip in the reader's convention (draw_video.py:42-56)
+    path = str(tmp_path / "Circle_num_8_control_SCP.json")
+    ro.dump_json(0, path)
+    with open(path) as f:
+        import json
+        assert tuple(json.load(f).keys()) == results.RESULT_KEYS
+    L = results.load_result(path, nx=6, nVeh=8, nObst=0, Hp=10, Nsim=Nsim, ticks_total=ro.ticks_total)
+    for k in ("vehiclePathFullRes", "controlPathFullRes", "controlPredictions", "trajectoryPredictions", "ReferenceTrajectory",
+              "MPC_delay_compensation_trajectory"):
+        np.testing.assert_array_equal(L[k], A[k])
+    assert L["initial_pos"].shape == (1, 2, 8, Nsim) and L["evaluations_obj_value"].shape == (Nsim, 1)
 
 
 def test_noise_is_keyed_per_instance_and_reproducible(mods, oracle):

@@ -12,7 +12,9 @@ from conftest import GOLDEN, golden_setup_inputs, load_golden
 from emu import emu
 
 capi = importlib.import_module("senquential-convex-programming-for-trajectory-planning_b200._capi")
-STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+ALL_STEP_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*_step*.npz")))
+STEP_FILES = [f for f in ALL_STEP_FILES if "frog" not in f]          # vehicle-pair rows only
+FROG_FILES = [f for f in ALL_STEP_FILES if "frog" in f]              # the reference's obstacle scenario (nVeh = 1, nObst = 22)
 FAST_FILES = [f for f in STEP_FILES if "hp50" not in f and "hp20" not in f]
 
 
@@ -294,3 +296,37 @@ def test_obstacle_rows_vs_oracle(oracle):
     base = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
                          ubars, params_for(G, max_scp_iter=1))
     assert np.abs(r["u"] - base["u"]).max() > 1e-4                        # the obstacles matter
+
+
+@pytest.mark.parametrize("fname", FROG_FILES)
+@pytest.mark.parametrize("reverse", [False, True])
+def test_frog_scenario_obstacle_rows_vs_reference(oracle, fname, reverse):
+    """The reference's own obstacle scenario (Scenarios.py:127-146; rows SCP_controller.py:106-114, 321-326): K2 against
+    the dense QP the reference logged, K4 teacher-forced against its per-iteration solutions and free-running against its
+    iteration count (obstacle_eval_mode = 1 reproduces the nesting of SCP_controller.py:249-263 under which a single
+    vehicle's obstacle constraints are never evaluated)."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    emu.config(nt=128, reverse=reverse)
+    dso, obst = G["sc_dsafeObstacles"][None], G["obst"][None]
+    for it in sorted(int(k.split("_")[1]) for k in G if k.startswith("Aineq_")):
+        P, q, A, b, lb, ub = emu.assemble_dense(S["g"], S["cterm"], S["H"], S["qv"], G["prev_u"][it][None],
+                                                G["sc_dsafeVehicles"][None], params_for(G), dsafe_obst=dso, obst=obst)
+        assert np.abs(P[0] - G[f"P_{it}"]).max() <= 1e-12 * np.abs(G[f"P_{it}"]).max()
+        assert np.abs(A[0] - G[f"Aineq_{it}"]).max() <= 1e-11 * np.abs(G[f"Aineq_{it}"]).max()
+        assert np.abs(b[0] - G[f"bineq_{it}"]).max() <= 1e-11 * np.abs(G[f"bineq_{it}"]).max()
+        np.testing.assert_array_equal(lb[0], G[f"lb_{it}"])
+        np.testing.assert_array_equal(ub[0], G[f"ub_{it}"])
+    nit = int(G["scp_iters"])
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    r = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]),
+                      rep(G["sc_dsafeVehicles"][None]), G["prev_u"][:nit], params_for(G, max_scp_iter=1, obstacle_eval_mode=1),
+                      dsafe_obst=rep(dso), obst=rep(obst))
+    for it in range(nit):
+        assert np.abs(r["u"][it] - G["x"][it][:-1]).max() < 1e-6, it
+        assert abs(r["log"][it, 0, 1] - G["SCP_ObjVal"][it]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][it]))
+    r = emu.scp_solve(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], G["u_warm"][None],
+                      params_for(G, obstacle_eval_mode=1), dsafe_obst=dso, obst=obst)
+    assert r["scp_iters"][0] == nit
+    assert np.abs(r["u"][0] - G["u_final"]).max() < 1e-6
+    assert np.abs(r["traj"][0] - G["Traj"]).max() < 1e-4

@@ -70,6 +70,13 @@ def test_setup_matches_reference(oracle, fname):
     assert abs(out["gamma0"][0] - G["gamma_0"].sum()) < 1e-13 * gscale
 
 
+def _obst(G):
+    """Obstacle arguments of a golden record (the frog scenario, Scenarios.py:127-146); {} for nObst = 0."""
+    if "sc_nObst" in G and int(G["sc_nObst"]) > 0:
+        return dict(dsafe_obst=G["sc_dsafeObstacles"], obst=G["obst"])
+    return {}
+
+
 def _setup(oracle, G):
     Hp = int(G["sc_Hp"])
     out = oracle.mpc_setup(*golden_setup_inputs(G), Hp=Hp, dt=float(G["sc_dt"]))
@@ -86,7 +93,7 @@ def test_dense_assembly_matches_reference(oracle, fname):
     for it in its:
         ubar = G["prev_u"][it]
         P, q, A, b, lb, ub = oracle.assemble_dense(S["g"], S["cterm"], S["H"], S["qv"], ubar, G["sc_dsafeVehicles"],
-                                                   float(G["sc_dsafeExtra"]), float(G["sc_uLim"]))
+                                                   float(G["sc_dsafeExtra"]), float(G["sc_uLim"]), **_obst(G))
         assert rel(P, G[f"P_{it}"]) < 1e-12
         assert rel(q, G[f"q_{it}"]) < 1e-11
         scale = np.abs(G[f"Aineq_{it}"]).max()
@@ -104,15 +111,17 @@ def test_evaluate_matches_reference(oracle, fname):
     """a9: QCQP_evaluate on the final u."""
     G = load_golden(fname)
     S = _setup(oracle, G)
+    # obstacle_mode=1: the reference's nesting of the obstacle check inside the v2 loop (SCP_controller.py:249-263)
     ev = oracle.qcqp_evaluate(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["u_final"], G["sc_dsafeVehicles"],
-                              float(G["sc_dsafeExtra"]))
+                              float(G["sc_dsafeExtra"]), obstacle_mode=1, **_obst(G))
     assert ev["feasible"] == bool(G["eval_feasible"])
     assert abs(ev["obj"] - float(G["eval_obj"])) <= 1e-9 * max(1.0, abs(float(G["eval_obj"])))
     assert abs(ev["max_violation"] - float(G["eval_max_violation"])) < 1e-9
     assert abs(ev["sum_violations"] - float(G["eval_sum_violations"])) < 1e-9
     fin = np.isfinite(G["eval_ci"])
     assert (np.isfinite(ev["ci"]) == fin).all()
-    assert np.abs(ev["ci"][fin] - G["eval_ci"][fin]).max() < 1e-9
+    if fin.any():                                                  # a single vehicle has no pair constraints
+        assert np.abs(ev["ci"][fin] - G["eval_ci"][fin]).max() < 1e-9
     # a11 forward_U
     pos = oracle.forward(S["g"], S["cterm"], G["u_final"])          # [nVeh,Hp,2]
     assert np.abs(np.transpose(pos, (1, 2, 0)) - G["Traj"]).max() < 1e-10
@@ -126,7 +135,8 @@ def test_scp_iterations_teacher_forced(oracle, fname):
     S = _setup(oracle, G)
     for it in range(int(G["scp_iters"])):
         P, q, A, b, lb, ub = oracle.assemble_dense(S["g"], S["cterm"], S["H"], S["qv"], G["prev_u"][it],
-                                                   G["sc_dsafeVehicles"], float(G["sc_dsafeExtra"]), float(G["sc_uLim"]))
+                                                   G["sc_dsafeVehicles"], float(G["sc_dsafeExtra"]), float(G["sc_uLim"]),
+                                                   **_obst(G))
         r = oracle.qp_boxed(P, q, A, b, lb, ub, opts=dict(abstol=1e-13, reltol=1e-13, feastol=1e-13), quad=True)
         assert r["status"] == 0
         assert np.abs(r["x"] - G["x"][it]).max() < 1e-11
@@ -144,7 +154,7 @@ def test_scp_loop_free_running(oracle, fname):
     S = _setup(oracle, G)
     r = oracle.scp_optimizer(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"], G["u_warm"],
                              dsafeExtra=float(G["sc_dsafeExtra"]), uLim=float(G["sc_uLim"]),
-                             opts=dict(abstol=1e-13, reltol=1e-13, feastol=1e-13), quad=True)
+                             opts=dict(abstol=1e-13, reltol=1e-13, feastol=1e-13), quad=True, obstacle_mode=1, **_obst(G))
     assert bool(r["log"][-1, 5]) == bool(G["feasible"][-1])
     if int(G["scp_iters"]) <= 5:                              # well away from the symmetric instability
         assert r["iters"] == int(G["scp_iters"])
