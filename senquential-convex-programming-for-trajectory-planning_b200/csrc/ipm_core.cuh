@@ -377,19 +377,19 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
         WARP_SECTION_END
         CTA_SYNC
         SCP_TIMER(6)
-        // X_IK = -sum_{J=K+1..I} X_IJ W_J.  Tile rows are paired (I, T+K-I) so that every warp carries the same
-        // number of tile products.
+        // X_IK = -sum_{J=K+1..I} X_IJ W_J: row ii (0-based below K) is a chain of ii + 1 tile products.  Rows are dealt
+        // to the warps longest first in snake order (w = 0..nw-1, nw-1..0, ...), which keeps the longest warp within
+        // one row of the mean for 4 and for 8 warps.
         WARP_SECTION(w, nw)
             WARP_PHASE(lane)
-                const int ngroup = (Tr + 1) >> 1;
-                for (int grp = w; grp < ngroup; grp += nw)
-                    for (int half = 0; half < 2; ++half) {
-                        const int ii = half == 0 ? grp : Tr - 1 - grp;          // 0-based tile row below K
-                        if (half == 1 && ii == grp) break;                        // odd Tr: the middle row once
-                        const int I = K + 1 + ii;
+                for (int pass = 0; pass * nw < Tr; ++pass) {
+                    const int q = pass * nw + ((pass & 1) ? nw - 1 - w : w);      // q-th longest row
+                    if (q < Tr) {
+                        const int ii = Tr - 1 - q, I = K + 1 + ii;
                         warp_tile_gemm_sum(lane, S + scp_tile_off(I, K), S + scp_tile_off(I, K + 1), SCP_TILE2, wbuf, SCP_TILE2,
                                            ii + 1, -1.0);
                     }
+                }
             WARP_PHASE_END
         WARP_SECTION_END
         CTA_SYNC

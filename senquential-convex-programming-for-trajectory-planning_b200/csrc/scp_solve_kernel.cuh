@@ -6,6 +6,9 @@
 #pragma once
 #include "scp_kernels.cuh"
 
+#ifndef SCP_FIXED_ALPHA
+#define SCP_FIXED_ALPHA 1      /* pair-block mode of the fixed-shape instantiations (tuning: 0 = entry by entry) */
+#endif
 #ifndef SCP_MIN_CTAS
 #define SCP_MIN_CTAS 2
 #endif
@@ -78,7 +81,7 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
     __shared__ int slot;
     scpb200_dims d = a.d;
     if (NVEH > 0) { d.nVeh = NVEH; d.Hp = HP; d.nObst = 0; }
-    const int alpha_slots = NVEH > 0 ? 1 : a.alpha_slots, want_H = NVEH > 0 ? 0 : a.want_H;
+    const int alpha_slots = NVEH > 0 ? SCP_FIXED_ALPHA : a.alpha_slots, want_H = NVEH > 0 ? 0 : a.want_H;
     Cta cta = {NT > 0 ? NT : (int)blockDim.x};
     ScpBump bp = scp_bump(sh, a.sh_lim, ALL_SHARED ? (double *)0 : a.gws + (size_t)blockIdx.x * a.gl_stride, ALL_SHARED);
     ScpMem s;
