@@ -356,7 +356,9 @@ def run_product(args):
             "e2e": {"value": e2e_all / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe: DMMA m8n8k4 (the FP64 tensor path) and DFMA share one "
+                         "peak on B200; the kernel is latency / issue bound far below it (DESIGN.md section 4)",
+                         "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach / fp64_peak, "traffic": ncu_traffic("k_scp_solve"),
                          "peak_source": "measured on this pool's B200 (tools/microbench_dmma.cu: DMMA m8n8k4 37.0 TFLOP/s, "
                                         "DFMA 36.5; profiles/r01_microbench*.txt); MEASURED_PEAKS.json has no FP64 entry",
@@ -369,7 +371,7 @@ def run_product(args):
                       "wall_s_bracket": t_wall, "p50_ms_per_mpc_step": float(np.median(step_ms)),
                       "plan": bs.plan()},
         }
-        if not args.skip_cpu and world >= 1:
+        if not args.skip_cpu and world == 1:                   # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             opts = dict(abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100)
             cq, cs, ci = cpu_controller_run(args.cpu_sample, nVeh, Hp, args.steps, 0, 0, cores, opts, args.noise_sigma, args.seed,
