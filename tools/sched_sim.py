@@ -4,7 +4,8 @@ bounds of a step (longest chain, total work / CTAs)."""
 import heapq, sys
 import numpy as np
 D = np.load(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/straggler_dump.npz")
-G = 296
+G = int(__import__('os').environ.get('SIM_CTAS', 296))
+MPIN = int(__import__('os').environ.get('SIM_MPIN', 99))      # rr: an instance that has done this many QPs is no longer parked
 A_US = float(sys.argv[2]) if len(sys.argv) > 2 else 47.0     # per interior-point iteration
 B_US = float(sys.argv[3]) if len(sys.argv) > 3 else 30.0     # per QP (linearise, evaluate, park / resume)
 steps = sorted(int(k.split("_")[1]) for k in D.files if k.startswith("scp_"))
@@ -35,7 +36,7 @@ def simulate(costs, order, policy, npinned=G // 2, pred=None, prio=None):
                 heapq.heappush(t_free, (t, c))
                 continue
             b = ring.popleft()
-            if b in pinned:
+            if b in pinned or done[b] >= MPIN:
                 t += costs[b][done[b]:].sum(); done[b] = len(costs[b])
             else:
                 t += costs[b][done[b]]; done[b] += 1
