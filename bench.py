@@ -175,6 +175,10 @@ def workload_config(args, B_per_gpu, note=None):
            "nVeh": args.nveh, "Hp": args.hp, "batch_per_gpu": B_per_gpu, "n1": args.nveh * args.hp + 1,
            "mc": args.hp * args.nveh * (args.nveh - 1) // 2, "l2": "flushed between timed steps (256 MiB write)",
            "qp_tolerances": {"abstol": 1e-10, "reltol": 1e-10, "feastol": 1e-9}}
+    if getattr(args, "trust_frac", 0) > 0:
+        cfg["trust_radius"] = f"{args.trust_frac} * uLim"
+    if getattr(args, "max_scp_iter", 0) > 0:
+        cfg["max_scp_iter"] = args.max_scp_iter
     if note:
         cfg["note"] = note
     return cfg
@@ -210,6 +214,10 @@ def run_product(args):
     p = capi.Params()
     capi.load().scpb200_default_params(C.byref(p))
     p.noise_sigma, p.seed, p.instance0 = args.noise_sigma, args.seed, inst0
+    if args.trust_frac > 0:
+        p.trust_radius = args.trust_frac * p.uLim
+    if args.max_scp_iter > 0:
+        p.max_scp_iter = args.max_scp_iter
     bs = batch.BatchSCP(B, nVeh, Hp, params=p, device=dev, keep_log=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     uMax, duLim = scen.MECH_LIMIT, scen.DU_LIM
@@ -240,7 +248,7 @@ def run_product(args):
     evs1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     qp_counts = torch.zeros(args.steps, dtype=torch.int64, device=dev)
     ipm_counts = torch.zeros(args.steps, dtype=torch.int64, device=dev)
-    stat_counts = torch.zeros(5, dtype=torch.int64, device=dev)   # instances x steps with status bits 1,2,4,8,16
+    stat_counts = torch.zeros(6, dtype=torch.int64, device=dev)   # instances x steps with status bits 1,2,4,8,16,32
     launches0 = bs.kernel_launches
     sampler = ClockSampler(local_rank)
     barrier()
@@ -258,7 +266,7 @@ def run_product(args):
         ev1[k].record()
         qp_counts[k] = bs.scp_iters.sum()
         ipm_counts[k] = bs.ipm_iters.sum()
-        stat_counts += torch.stack([((bs.status >> i) & 1).sum() for i in range(5)])
+        stat_counts += torch.stack([((bs.status >> i) & 1).sum() for i in range(6)])
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -366,7 +374,7 @@ def run_product(args):
             "roofline_assembly": asm,
             "stats": {"qps_total": qps_all, "ipm_iterations_total": ipm_all, "qp_per_instance_step": qps_all / (world * B * args.steps),
                       "ipm_per_qp": ipm_all / max(1, qps_all),
-                      "status_counts_rank0": dict(zip(["qp_maxiter", "qp_pivot", "scp_maxiter", "infeasible", "setup"],
+                      "status_counts_rank0": dict(zip(["qp_maxiter", "qp_pivot", "scp_maxiter", "infeasible", "setup", "qp_dres_floor"],
                                                       [int(v) for v in stat_counts.cpu()])),
                       "wall_s_bracket": t_wall, "p50_ms_per_mpc_step": float(np.median(step_ms)),
                       "plan": bs.plan()},
@@ -399,6 +407,9 @@ def main():
     ap.add_argument("--step-lo", dest="step_lo", type=int, default=4)
     ap.add_argument("--step-hi", dest="step_hi", type=int, default=7)
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=256, help="instances of the CPU baseline sample")
+    ap.add_argument("--trust-radius-frac", dest="trust_frac", type=float, default=0.0,
+                    help="BASELINE configs[3]: trust region |u - ubar|_inf <= frac * uLim folded into the box (0 = off, the reference)")
+    ap.add_argument("--max-scp-iter", dest="max_scp_iter", type=int, default=0, help="SCP iteration cap (0 = the reference's 20)")
     ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true")
     ap.add_argument("--skip-assembly", dest="skip_assembly", action="store_true")
     args = ap.parse_args()

@@ -43,6 +43,9 @@ extern "C" {
 #define SCPB200_ST_SCP_MAXITER 4  /* SCP loop ended on max_scp_iter, not on the stop test */
 #define SCPB200_ST_INFEASIBLE 8   /* final iterate violates a collision constraint by more than constraint_tol */
 #define SCPB200_ST_SETUP 16       /* set-up failed for this instance (expm / sampler index) */
+#define SCPB200_ST_QP_DRES_FLOOR 32 /* some QP was accepted at the precision floor of its dual residual: gap and primal
+                                     * residual within tolerance, dual residual within 100 qp_feastol and no longer
+                                     * decreasing (further iterations only degrade it) */
 
 typedef struct scpb200_dims {
     int32_t B;      /* instances (independent scenarios / noise samples) */

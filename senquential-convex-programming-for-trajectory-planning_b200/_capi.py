@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCPB200_LIB") or os.path.join(HERE, "libscpb200.so")   # override: kernel-tuning builds only
 
 LOG_W = 10
-ST_QP_MAXITER, ST_QP_PIVOT, ST_SCP_MAXITER, ST_INFEASIBLE, ST_SETUP = 1, 2, 4, 8, 16
+ST_QP_MAXITER, ST_QP_PIVOT, ST_SCP_MAXITER, ST_INFEASIBLE, ST_SETUP, ST_QP_DRES_FLOOR = 1, 2, 4, 8, 16, 32
 
 
 class Dims(C.Structure):

@@ -1,8 +1,8 @@
 """Build libscpb200.so in-tree with nvcc for sm_100a (the only target).
 
-The library is four translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
-dimensions (scp_solve_generic.cu) and with the literal dimensions of BASELINE.json's headline shape at two CTA widths
-(scp_solve_fixed.cu, compiled twice) — compiled in parallel and linked into one shared object."""
+The library is five translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
+dimensions (scp_solve_generic.cu) and with the literal dimensions of the shapes BASELINE.json names (scp_solve_fixed.cu:
+8 vehicles x Hp 10 at two CTA widths, 8 vehicles x Hp 20) — compiled in parallel and linked into one shared object."""
 from __future__ import annotations
 
 import os
@@ -17,8 +17,9 @@ OBJ = os.path.join(os.path.dirname(HERE), "gpurun_out", "build_obj")
 # (object name, source, extra flags)
 UNITS = [("scpb200.o", "scpb200.cu", []),
          ("scp_solve_generic.o", "scp_solve_generic.cu", []),
-         ("scp_solve_fixed_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_NT=256"]),
-         ("scp_solve_fixed_128.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_NT=128"])]
+         ("scp_solve_v8h10_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=10", "-DSCP_FIXED_NT=256"]),
+         ("scp_solve_v8h10_128.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=10", "-DSCP_FIXED_NT=128"]),
+         ("scp_solve_v8h20_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=256"])]
 DEPS = ["scp_common.cuh", "ipm_core.cuh", "ops_pair.cuh", "ops_dense.cuh", "scp_kernels.cuh", "scp_solve_kernel.cuh",
         "scpb200.cu", "scp_solve_generic.cu", "scp_solve_fixed.cu", os.path.join("..", "..", "include", "scpb200.h")]
 

@@ -803,16 +803,17 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             ctl.max_iter = p.qp_warm_max_iter > 0 ? p.qp_warm_max_iter : cap;
             ipm_solve(cta, op, m, ctl, &res);
             ctl.max_iter = cap;
-            if (res.status) { ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
+            if (res.status & SCPB200_ST_QP_MAXITER) { ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
         } else {
             ipm_solve(cta, op, m, ctl, &res);
         }
         // a warm-started QP that converged before it reached the iteration a new iterate is taken from leaves the old
         // one in place: it was a good start for this QP and the next one is closer still (SCP is converging)
-        snap_valid = res.snap_saved || (ctl.warm && res.status == 0 && snap_valid);
+        snap_valid = res.snap_saved || (ctl.warm && !(res.status & SCPB200_ST_QP_MAXITER) && snap_valid);
         ipm_total += res.iters;
         if (res.status & SCPB200_ST_QP_MAXITER) st |= SCPB200_ST_QP_MAXITER;
         if (res.status & SCPB200_ST_QP_PIVOT) st |= SCPB200_ST_QP_PIVOT;
+        if (res.status & SCPB200_ST_QP_DRES_FLOOR) st |= SCPB200_ST_QP_DRES_FLOOR;
         const double slack = m.x[n];
         CTA_PHASE(tid)
             for (int c = tid; c < n; c += cta.nt) s.ucur[c] = m.x[c];
@@ -831,6 +832,9 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
                     double *L = io.log + ((size_t)b * p.max_scp_iter + it) * SCPB200_LOG_W;
                     L[0] = slack; L[1] = fval; L[2] = ev.obj; L[3] = delta_hat; L[4] = delta; L[5] = ev.feasible;
                     L[6] = ev.max_violation; L[7] = ev.sum_violations; L[8] = res.iters; L[9] = res.status;
+#ifdef SCP_DIAG_LOG     /* tuning builds: where did the interior-point method stop */
+                    L[5] = res.dres; L[6] = res.pres; L[7] = res.relgap; L[3] = res.gap;
+#endif
                 }
             CTA_PHASE_END
         }

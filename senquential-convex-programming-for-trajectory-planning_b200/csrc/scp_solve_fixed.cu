@@ -1,14 +1,17 @@
-// scp_solve_fixed.cu — K4 instantiated with literal dimensions and CTA width for the shape BASELINE.json's headline
-// configuration names (8 vehicles, Hp = 10, no obstacles).  Compiled once per CTA width (-DSCP_FIXED_NT=256 / 128).
+// scp_solve_fixed.cu — K4 instantiated with literal dimensions and CTA width for the shapes BASELINE.json names:
+// 8 vehicles, no obstacles, Hp = 10 (configs[1]; -DSCP_FIXED_HP=10 -DSCP_FIXED_NT=256 / 128) and Hp = 20 (configs[2];
+// -DSCP_FIXED_HP=20 -DSCP_FIXED_NT=256).  One compilation per (Hp, CTA width).
 #include "scp_solve_kernel.cuh"
 
-#ifndef SCP_FIXED_NT
-#error "compile with -DSCP_FIXED_NT=256 or 128"
+#if !defined(SCP_FIXED_NT) || !defined(SCP_FIXED_HP)
+#error "compile with -DSCP_FIXED_HP=10|20 -DSCP_FIXED_NT=256|128"
 #endif
-#if SCP_FIXED_NT == 256
+#if SCP_FIXED_HP == 10 && SCP_FIXED_NT == 256
 SCP_DEFINE_KERNEL_ENTRY(scp_entry_v8h10_t256, true, 8, 10, 256)
-#elif SCP_FIXED_NT == 128
+#elif SCP_FIXED_HP == 10 && SCP_FIXED_NT == 128
 SCP_DEFINE_KERNEL_ENTRY(scp_entry_v8h10_t128, true, 8, 10, 128)
+#elif SCP_FIXED_HP == 20 && SCP_FIXED_NT == 256
+SCP_DEFINE_KERNEL_ENTRY(scp_entry_v8h20_t256, true, 8, 20, 256)
 #else
-#error "unsupported SCP_FIXED_NT"
+#error "unsupported (SCP_FIXED_HP, SCP_FIXED_NT)"
 #endif

@@ -74,14 +74,14 @@ __device__ __forceinline__ int queue_pop(const WorkQueue &q)
 // (n, n1, tile counts, divisions by Hp, strided loops over the CTA) into constants and unrolls the short loops; in
 // its generic form the kernel executes ~20 instructions of addressing and loop control per FP64 operation.
 template <bool ALL_SHARED, int NVEH, int HP, int NT>
-__global__ void __launch_bounds__(NT > 0 ? NT : SCP_MAX_THREADS, (NT > 0 && NT <= 128) ? 3 : SCP_MIN_CTAS)
+__global__ void __launch_bounds__(NT > 0 ? NT : SCP_MAX_THREADS, (NT > 0 && NT <= 128) ? 3 : (HP > 10 ? 1 : SCP_MIN_CTAS))
 k_scp_solve(const __grid_constant__ ScpKernelArgs a)
 {
     extern __shared__ double sh[];
     __shared__ int slot;
     scpb200_dims d = a.d;
     if (NVEH > 0) { d.nVeh = NVEH; d.Hp = HP; d.nObst = 0; }
-    const int alpha_slots = NVEH > 0 ? SCP_FIXED_ALPHA : a.alpha_slots, want_H = NVEH > 0 ? 0 : a.want_H;
+    const int alpha_slots = NVEH > 0 ? SCP_FIXED_ALPHA : a.alpha_slots, want_H = (NVEH > 0 && HP <= 10) ? 0 : a.want_H;
     Cta cta = {NT > 0 ? NT : (int)blockDim.x};
     ScpBump bp = scp_bump(sh, a.sh_lim, ALL_SHARED ? (double *)0 : a.gws + (size_t)blockIdx.x * a.gl_stride, ALL_SHARED);
     ScpMem s;
@@ -149,3 +149,4 @@ extern "C" const ScpKernelEntry *scp_entry_generic_shared(void);
 extern "C" const ScpKernelEntry *scp_entry_generic_global(void);
 extern "C" const ScpKernelEntry *scp_entry_v8h10_t256(void);       // BASELINE.json configs[1]: 8 vehicles, Hp = 10
 extern "C" const ScpKernelEntry *scp_entry_v8h10_t128(void);
+extern "C" const ScpKernelEntry *scp_entry_v8h20_t256(void);       // BASELINE.json configs[2]: 8 vehicles, Hp = 20

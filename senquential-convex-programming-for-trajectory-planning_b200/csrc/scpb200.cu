@@ -410,9 +410,10 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
         SolvePlan cand = *pl;
         // the fixed-shape instantiations cover the layout without shared-resident cost blocks
         const ScpKernelEntry *ks = scp_entry_generic_shared();
-        if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && Hp == 10 && nObst == 0 && slots == 1 && want_H == 0) {
-            if (threads == 256) ks = scp_entry_v8h10_t256();
-            else if (threads == 128) ks = scp_entry_v8h10_t128();
+        if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && nObst == 0 && slots == 1) {
+            if (Hp == 10 && threads == 256 && want_H == 0) ks = scp_entry_v8h10_t256();
+            else if (Hp == 10 && threads == 128 && want_H == 0) ks = scp_entry_v8h10_t128();
+            else if (Hp == 20 && threads == 256) ks = scp_entry_v8h20_t256();          // either placement of the cost blocks
         }
         int rc = plan_common(ks->prepare, scp_entry_generic_global()->prepare, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand);
         if (rc) return rc;
@@ -706,10 +707,10 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
 // tuning builds only: read (and clear) the per-region cycle counters
 extern "C" int scpb200_debug_read_timers(unsigned long long *out32)
 {
-    const ScpKernelEntry *es[4] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
-                                   scp_entry_v8h10_t128()};
+    const ScpKernelEntry *es[5] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
+                                   scp_entry_v8h10_t128(), scp_entry_v8h20_t256()};
     for (int i = 0; i < 32; ++i) out32[i] = 0;
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 5; ++e) {
         unsigned long long part[32];
         if (!es[e]->read_timers || es[e]->read_timers(part)) return set_err(SCPB200_ERR_CUDA, "timer read failed");
         for (int i = 0; i < 32; ++i) out32[i] += part[i];

@@ -137,7 +137,8 @@ def test_dense_qp_entry_vs_extended_precision_minimiser(mods, oracle, fname):
     x, fval, st, zA = host(r["x"]), host(r["fval"]), host(r["status"]), host(r["zA"])
     for j, it in enumerate(its):
         xs = G["x"][it]
-        assert st[j] == 0, (it, st[j], host(r["iters"])[j])
+        # converged, possibly accepted at the precision floor of the dual residual (the accuracy checks below hold either way)
+        assert (st[j] & ~mods["capi"].ST_QP_DRES_FLOOR) == 0, (it, st[j], host(r["iters"])[j])
         assert np.abs(x[j] - xs).max() < 1e-6
         f_ref = 0.5 * xs @ P[j] @ xs + q[j] @ xs
         assert abs(fval[j] - f_ref) <= 1e-6 * max(1.0, abs(f_ref))
