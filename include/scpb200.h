@@ -68,7 +68,7 @@ typedef struct scpb200_params {
     int32_t obstacle_eval_mode; /* 0: every (v,o,k) once; 1: the reference's nesting (SCP_controller.py:249-263) */
     /* interior-point controls (the reference delegates these to its third-party solver) */
     double qp_abstol, qp_reltol, qp_feastol; /* CVXOPT-style stopping rule; defaults 1e-10, 1e-10, 1e-9 */
-    double qp_dual_reg;      /* proximal regularisation of s/z in the normal matrix (default 1e-12) */
+    double qp_dual_reg;      /* proximal regularisation of s/z in the normal matrix (default 1e-11: no pivot breakdown up to Hp = 50, fewer iterations than 1e-12, and u within 2e-8 of the extended-precision minimiser where 1e-10 leaves 1e-6; swept 1e-12 ... 1e-9 on B200) */
     double inf_bound;        /* |bound| >= inf_bound means "no bound" (default 1e20, Gurobi's convention) */
     int32_t ipm_max_iter;    /* default 60 */
     int32_t qp_warm_start;   /* scpb200_scp_solve only: start the QP of SCP iteration k+1 from an interior iterate of QP k
@@ -86,7 +86,9 @@ typedef struct scpb200_params {
     int32_t qp_warm_carry;   /* 1: the first QP of a call starts from the iterate the previous call on the same workspace
                               * left for that instance (consecutive MPC steps of the same scenarios; the workspace must be
                               * zero-initialised before its first use).  Default 0: every call starts cold. */
-    int32_t reserved2;
+    int32_t qp_dres_floor_factor; /* a QP whose gap and primal residual have converged is accepted when its dual residual is
+                              * within this factor of qp_feastol and no longer decreasing (SCPB200_ST_QP_DRES_FLOOR);
+                              * 0 = never (iterate to ipm_max_iter).  Default 100. */
 } scpb200_params;
 
 /* width of one row of the per-iteration log of scpb200_scp_solve (SCP_controller.py:169-189, scalar fields) */

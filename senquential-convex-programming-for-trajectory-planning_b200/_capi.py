@@ -30,7 +30,7 @@ class Params(C.Structure):
         ("trust_radius", C.c_double), ("noise_sigma", C.c_double), ("seed", C.c_uint64),
         ("instance0", C.c_uint32), ("noise_counter", C.c_uint32),
         ("qp_warm_relgap", C.c_double), ("qp_warm_max_iter", C.c_int32), ("qp_warm_min_iter", C.c_int32),
-        ("qp_warm_carry", C.c_int32), ("reserved2", C.c_int32),
+        ("qp_warm_carry", C.c_int32), ("qp_dres_floor_factor", C.c_int32),
     ]
 
 
@@ -41,9 +41,10 @@ def default_params_py() -> Params:
     p.dt, p.uLim, p.dsafeExtra, p.delta_tol = 0.4, math.pi / 180.0 * 3.0, 1.0, 1e-3
     p.omega_weight, p.omega_ub, p.constraint_tol = 1e5, 1e25, 2 * 2.1 * 1e-3
     p.max_scp_iter, p.obstacle_eval_mode = 20, 0
-    p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-10, 1e-10, 1e-9, 1e-12, 1e20
+    p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-10, 1e-10, 1e-9, 1e-11, 1e20
     p.ipm_max_iter, p.trust_radius, p.noise_sigma, p.seed, p.instance0, p.noise_counter = 60, 1e308, 0.0, 0, 0, 0
     p.qp_warm_start, p.qp_warm_relgap, p.qp_warm_max_iter, p.qp_warm_min_iter, p.qp_warm_carry = 1, 1.0, 30, 2, 0
+    p.qp_dres_floor_factor = 100
     return p
 
 

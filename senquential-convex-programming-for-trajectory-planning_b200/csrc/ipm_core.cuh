@@ -33,6 +33,7 @@
 
 struct IpmCtl {
     double abstol, reltol, feastol, dual_reg, inf_bound;
+    double dres_floor;   // accept at the precision floor of the dual residual when it is <= dres_floor (0 = never)
     int max_iter;
     // Warm start across the QPs of one SCP loop (consecutive QPs differ only in the linearisation point):
     //   snap      global memory for one interior iterate (x, s, z of every row; ipm_snap_doubles()), or null
@@ -604,9 +605,9 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         const bool gap_ok = gap <= ctl.abstol || (relgap >= 0.0 && relgap <= ctl.reltol);
         if (pres <= ctl.feastol && dres <= ctl.feastol && gap_ok) { status = 0; break; }
         // Precision floor of the dual residual: gap and primal residual have converged, the dual residual is within
-        // 100 feastol and no longer decreasing.  Iterating on drives s.z to underflow and the residual back up (measured
+        // qp_dres_floor_factor x feastol and no longer decreasing.  Iterating on drives s.z to underflow and the residual back up (measured
         // at Hp = 20 / 50: gap 1e-90, dres 1e-7 after 60 iterations); accept the iterate and say so.
-        if (gap_ok && pres <= ctl.feastol && dres <= 100.0 * ctl.feastol && iters > 0 && dres >= 0.5 * dres_prev) {
+        if (gap_ok && pres <= ctl.feastol && dres <= ctl.dres_floor && iters > 0 && dres >= 0.5 * dres_prev) {
             status = SCPB200_ST_QP_DRES_FLOOR;
             break;
         }

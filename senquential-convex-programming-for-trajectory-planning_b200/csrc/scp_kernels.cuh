@@ -717,6 +717,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     IpmCtl ctl;
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+    ctl.dres_floor = p.qp_dres_floor_factor * p.qp_feastol;
     ctl.snap = (io.snap && p.qp_warm_start) ? io.snap + (size_t)b * ipm_snap_doubles(m.n1p, mc) : 0;
     ctl.snap_relgap = p.qp_warm_relgap;
     ctl.warm = 0;
@@ -879,6 +880,7 @@ SCP_FN void qp_solve_instance(Cta &cta, const scpb200_params &p, int n1, int mc,
     IpmCtl ctl;
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
+    ctl.dres_floor = p.qp_dres_floor_factor * p.qp_feastol;
     ctl.snap = 0; ctl.snap_relgap = 0.0; ctl.warm = 0; ctl.snap_min_iter = 0;
     DenseOp op;
     op.n1 = n1; op.mc = mc;

@@ -39,7 +39,7 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->qp_abstol = 1e-10;
     p->qp_reltol = 1e-10;
     p->qp_feastol = 1e-9;
-    p->qp_dual_reg = 1e-12;
+    p->qp_dual_reg = 1e-11;
     p->inf_bound = 1e20;
     p->ipm_max_iter = 60;
     p->trust_radius = 1e308;
@@ -52,6 +52,7 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->qp_warm_max_iter = 30;
     p->qp_warm_min_iter = 2;
     p->qp_warm_carry = 0;
+    p->qp_dres_floor_factor = 100;
 }
 
 extern "C" int scpb200_device_count(void)

@@ -8,11 +8,12 @@ capi = importlib.import_module(PKG + "._capi"); batch = importlib.import_module(
 ap = argparse.ArgumentParser()
 ap.add_argument("--hp", type=int, default=50); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--trust", type=float, default=0.0); ap.add_argument("--steps", type=int, default=4)
-ap.add_argument("--msi", type=int, default=20)
+ap.add_argument("--msi", type=int, default=20); ap.add_argument("--dual-reg", dest="dreg", type=float, default=0.0)
 a = ap.parse_args()
 cb = scen.circle_batch(a.batch, Hp=a.hp, step_lo=4, step_hi=7)
 p = capi.Params(); capi.load().scpb200_default_params(C.byref(p)); p.max_scp_iter = a.msi
 if a.trust > 0: p.trust_radius = a.trust * p.uLim
+if a.dreg > 0: p.qp_dual_reg = a.dreg
 bs = batch.BatchSCP(a.batch, 8, a.hp, params=p)
 bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((a.batch, 8 * a.hp)))
 for s in range(a.steps):
