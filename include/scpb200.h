@@ -82,7 +82,7 @@ typedef struct scpb200_params {
     uint32_t noise_counter;  /* draw counter (e.g. the MPC step index) */
     double qp_warm_relgap;   /* the iterate kept for the next QP is the first with relative gap <= this (default 1.0: an early, well-centred iterate; measured best on the 1024-instance benchmark) */
     int32_t qp_warm_max_iter; /* a warm-started QP not converged after this many iterations restarts cold (default 30) */
-    int32_t qp_warm_min_iter; /* ... and not before this iteration of the QP it is taken from (default 2) */
+    int32_t qp_warm_min_iter; /* ... and not before this iteration of the QP it is taken from (default 5; swept 1..6 with relgap 0.1..100 on the 1024-instance benchmark, profiles/r01_sweep_warm_start.txt) */
     int32_t qp_warm_carry;   /* 1: the first QP of a call starts from the iterate the previous call on the same workspace
                               * left for that instance (consecutive MPC steps of the same scenarios; the workspace must be
                               * zero-initialised before its first use).  Default 0: every call starts cold. */

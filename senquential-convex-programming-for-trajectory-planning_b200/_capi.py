@@ -43,7 +43,7 @@ def default_params_py() -> Params:
     p.max_scp_iter, p.obstacle_eval_mode = 20, 0
     p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-10, 1e-10, 1e-9, 1e-11, 1e20
     p.ipm_max_iter, p.trust_radius, p.noise_sigma, p.seed, p.instance0, p.noise_counter = 60, 1e308, 0.0, 0, 0, 0
-    p.qp_warm_start, p.qp_warm_relgap, p.qp_warm_max_iter, p.qp_warm_min_iter, p.qp_warm_carry = 1, 1.0, 30, 2, 0
+    p.qp_warm_start, p.qp_warm_relgap, p.qp_warm_max_iter, p.qp_warm_min_iter, p.qp_warm_carry = 1, 1.0, 30, 5, 0
     p.qp_dres_floor_factor = 100
     return p
 

@@ -50,7 +50,7 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->qp_warm_start = 1;
     p->qp_warm_relgap = 1.0;
     p->qp_warm_max_iter = 30;
-    p->qp_warm_min_iter = 2;
+    p->qp_warm_min_iter = 5;
     p->qp_warm_carry = 0;
     p->qp_dres_floor_factor = 100;
 }
