@@ -58,7 +58,7 @@ struct IpmMem {
     double *lb, *sL, *zL, *dsL, *dzL, *ccL, *eL;         // [n1p]   x >= lb rows
     double *dinv;   // [n1p]             reciprocal pivots of the factor
     double *wbuf;   // [max(T*64, 4*n1p)] tile scratch of the inversion sweep / partial sums of the solves
-    double *red;    // [8 * SCP_MAX_WARPS] reduction scratch
+    double *red;    // [SCP_RED_DOUBLES] reduction scratch (double-buffered, see scp_common.cuh)
     double *t8;     // [16] tile-solve scratch (8) + flags
 };
 

@@ -36,18 +36,28 @@
 #define SCP_TILE2 64
 
 // ------------------------------------------------------------------------------------------------ phases
+// Reductions: a reducing phase leaves one partial per warp in `red`; after the phase's barrier every thread folds them.
+// Nothing separates those reads from the NEXT reducing phase's writes but that phase's own work, so a warp held up
+// right after the barrier could read partials of the following reduction (observed on B200 as rounding-level,
+// schedule-dependent differences in ~1 of 1000 instances).  The scratch is therefore double-buffered: consecutive
+// reductions alternate between two sets of SCP_RED_SLOTS slots (`Cta::flip`), and a late reader is always at most one
+// reduction behind its writers' barrier.
+#define SCP_RED_SLOTS 8
+#define SCP_RED_DOUBLES (2 * SCP_RED_SLOTS * SCP_MAX_WARPS)
 #if SCP_DEVICE_BUILD
 struct Cta {
     int nt;
+    int flip;      // 0 or SCP_RED_SLOTS: which half of the reduction scratch the current reduction uses
 };
 #define CTA_PHASE(tid) { const int tid = (int)threadIdx.x;
 #define CTA_PHASE_END } __syncthreads();
-#define CTA_RED_BEGIN(cta, nslots)
+#define CTA_RED_BEGIN(cta, nslots) (cta).flip ^= SCP_RED_SLOTS;
 #define CTA_PHASE_END_RED(cta, red, nslots) } __syncthreads();
 #else
 #define SCP_EMU_MAXNT 1024
 struct Cta {
     int nt;
+    int flip;                              // as on the device
     int reverse;                           // emulate threads in descending order
     double part[8 * SCP_EMU_MAXNT];        // per-thread partials of the reduction slots
     int part_kind[8];                      // 0 = sum, 1 = max
@@ -56,6 +66,7 @@ static inline int scp_emu_tid(const Cta &c, int i) { return c.reverse ? c.nt - 1
 #define CTA_PHASE(tid) for (int tid##_i = 0; tid##_i < cta.nt; ++tid##_i) { const int tid = scp_emu_tid(cta, tid##_i);
 #define CTA_PHASE_END }
 #define CTA_RED_BEGIN(cta, nslots)                                                     \
+    (cta).flip ^= SCP_RED_SLOTS;                                                       \
     for (int s_ = 0; s_ < (nslots); ++s_)                                              \
         for (int t_ = 0; t_ < (cta).nt; ++t_) (cta).part[s_ * SCP_EMU_MAXNT + t_] = 0.0;
 // butterfly in the device's order: v[l] (+|max)= v[l ^ off], off = 16..1; lane 0 of each warp publishes
@@ -70,7 +81,7 @@ static inline int scp_emu_tid(const Cta &c, int i) { return c.reverse ? c.nt - 1
                     n_[l_] = (cta).part_kind[s_] ? fmax(v_[l_], v_[l_ ^ off_]) : v_[l_] + v_[l_ ^ off_]; \
                 for (int l_ = 0; l_ < 32; ++l_) v_[l_] = n_[l_];                       \
             }                                                                          \
-            (red)[s_ * SCP_MAX_WARPS + w_] = v_[0];                                    \
+            (red)[(s_ + (cta).flip) * SCP_MAX_WARPS + w_] = v_[0];                     \
         }
 #endif
 
@@ -111,12 +122,12 @@ SCP_FN double scp_warp_max(double v)
 #define CTA_RED_SUM(cta, red, slot, tid, val)                                 \
     {                                                                         \
         double r_ = scp_warp_sum(val);                                        \
-        if (((tid) & 31) == 0) (red)[(slot) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
+        if (((tid) & 31) == 0) (red)[((slot) + (cta).flip) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
     }
 #define CTA_RED_MAX(cta, red, slot, tid, val)                                 \
     {                                                                         \
         double r_ = scp_warp_max(val);                                        \
-        if (((tid) & 31) == 0) (red)[(slot) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
+        if (((tid) & 31) == 0) (red)[((slot) + (cta).flip) * SCP_MAX_WARPS + ((tid) >> 5)] = r_; \
     }
 #else
 #define CTA_RED_SUM(cta, red, slot, tid, val) { (cta).part_kind[slot] = 0; (cta).part[(slot) * SCP_EMU_MAXNT + (tid)] = (val); }
@@ -128,14 +139,14 @@ SCP_FN double cta_red_sum(const Cta &cta, const double *red, int slot)
 {
     double t = 0.0;
     const int nw = cta.nt >> 5;
-    for (int w = 0; w < nw; ++w) t += red[slot * SCP_MAX_WARPS + w];
+    for (int w = 0; w < nw; ++w) t += red[(slot + cta.flip) * SCP_MAX_WARPS + w];
     return t;
 }
 SCP_FN double cta_red_max(const Cta &cta, const double *red, int slot)
 {
-    double t = red[slot * SCP_MAX_WARPS];
+    double t = red[(slot + cta.flip) * SCP_MAX_WARPS];
     const int nw = cta.nt >> 5;
-    for (int w = 1; w < nw; ++w) t = fmax(t, red[slot * SCP_MAX_WARPS + w]);
+    for (int w = 1; w < nw; ++w) t = fmax(t, red[(slot + cta.flip) * SCP_MAX_WARPS + w]);
     return t;
 }
 

@@ -599,7 +599,7 @@ SCP_HDFN ScpBump scp_bump(double *sh, size_t sh_lim, double *gl, bool all_shared
 SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc)
 {
     m.n1 = n1; m.n1p = scp_round_up(n1, SCP_TILE); m.T = m.n1p / SCP_TILE; m.mc = mc;
-    m.red = bp.take(8 * SCP_MAX_WARPS);
+    m.red = bp.take(SCP_RED_DOUBLES);
     m.t8 = bp.take(16);
     m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
     m.dinv = bp.take(m.n1p);

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) k_mpc_setup(scpb200_dims d, scpb200_param
                                                    double *cterm, double *H, double *qv, double *gamma0, double *abe,
                                                    int32_t *setup_status)
 {
-    __shared__ double red[8 * SCP_MAX_WARPS];
+    __shared__ double red[SCP_RED_DOUBLES];
     __shared__ int flag;
     Cta cta = {(int)blockDim.x};
     for (int b = blockIdx.x; b < d.B; b += gridDim.x)
@@ -373,22 +373,23 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
 // Launch shape.  A 128-thread CTA runs an interior-point iteration only ~7 % slower than a 256-thread one (the
 // iteration is a chain of short dependent phases), and three of them fit an SM where the register file holds two
 // 256-thread CTAs.  Measured on B200 (profiles/r01_sweep_shapes_*.txt, profiles/README.md): a batch that keeps every CTA
-// busy for the whole step gains 23-26 % from 3 x 128 (8192 instances), the 1024-instance benchmark 3 %; batches with
-// fewer than two instances per CTA end on the longest chain of QPs of one instance and keep 2 x 256.
-// SCPB200_THREADS overrides.
-#define SCP_THROUGHPUT_BATCH 888
+// busy for the whole step gains 23-26 % from 3 x 128 (8192 instances), the 1024-instance benchmark 3 %.  The shape is
+// chosen from the problem dimensions alone, never from the batch size: the CTA width fixes the order of the
+// reductions, and per-instance results must not depend on how a batch is sharded.
+// SCPB200_THREADS overrides (tuning).
 static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
 {
     const int forced = env_int("SCPB200_THREADS", 0);
     if (forced > 0) return plan_scp_threads(d, forced, pl);
-    int rc = plan_scp_threads(d, 256, pl);
-    if (rc || d->B < SCP_THROUGHPUT_BATCH) return rc;
-    SolvePlan narrow = *pl;
-    rc = plan_scp_threads(d, 128, &narrow);
+    scpb200_dims big = *d;
+    big.B = 1 << 20;                                       // CTAs per SM of either shape, unclipped by the batch
+    SolvePlan wide = *pl, narrow = *pl;
+    int rc = plan_scp_threads(&big, 256, &wide);
     if (rc) return rc;
-    if (narrow.all_shared && narrow.grid > pl->grid) *pl = narrow;
-    else rc = plan_scp_threads(d, 256, pl);            // restore the function attributes of the chosen shape
-    return rc;
+    rc = plan_scp_threads(&big, 128, &narrow);
+    if (rc) return rc;
+    const int threads = (narrow.all_shared && narrow.grid > wide.grid) ? 128 : 256;
+    return plan_scp_threads(d, threads, pl);               // also leaves the function attributes of the chosen shape
 }
 
 static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
@@ -548,7 +549,7 @@ extern "C" int scpb200_qcqp_evaluate(const scpb200_dims *d, const scpb200_params
     DevInfo di;
     rc = dev_info(&di);
     if (rc) return rc;
-    const size_t smem = ((size_t)d->nVeh * d->Hp * 2 + 8 * SCP_MAX_WARPS) * 8;
+    const size_t smem = ((size_t)d->nVeh * d->Hp * 2 + SCP_RED_DOUBLES) * 8;
     if (smem > (size_t)di.smem_optin) return set_err(SCPB200_ERR_SIZE, "evaluate: positions exceed shared memory");
     CUDA_TRY(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = d->B < di.sms * 8 ? d->B : di.sms * 8;

@@ -36,7 +36,7 @@ extern "C" int emu_mpc_setup(const scpb200_dims *d, const scpb200_params *p, con
                              double *qv, double *gamma0, double *abe, int32_t *setup_status)
 {
     Cta *cta = new_cta();
-    std::vector<double> red(8 * SCP_MAX_WARPS);
+    std::vector<double> red(SCP_RED_DOUBLES);
     int flag = 0;
     for (int b = 0; b < d->B; ++b)
         scp_setup_instance(*cta, *d, *p, b, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe, setup_status,
@@ -75,7 +75,7 @@ extern "C" int emu_qcqp_evaluate(const scpb200_dims *d, const scpb200_params *p,
 {
     Cta *cta = new_cta();
     const int nVeh = d->nVeh, Hp = d->Hp, nObst = d->nObst, n = nVeh * Hp;
-    std::vector<double> pos((size_t)n * 2), red(8 * SCP_MAX_WARPS);
+    std::vector<double> pos((size_t)n * 2), red(SCP_RED_DOUBLES);
     for (int b = 0; b < d->B; ++b) {
         ScpEval ev;
         scp_evaluate(*cta, nVeh, Hp, nObst, g + (size_t)b * n * 2, cterm + (size_t)b * n * 2, H + (size_t)b * n * Hp,
@@ -138,9 +138,19 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
         io.quantum = atoi(qe);
         io.state = (double *)calloc((size_t)d->B * SCP_STATE_W, sizeof(double));
         char *done = (char *)calloc(d->B, 1);
+        // SCPB200_EMU_POISON=1: every invocation starts from a working set full of NaNs, as a CTA that last worked on
+        // another instance would (nothing an invocation reads may be left over from the one before)
+        const char *pe = getenv("SCPB200_EMU_POISON");
+        const bool poison = pe && atoi(pe) > 0;
         for (int live = d->B; live > 0;)
-            for (int b = 0; b < d->B; ++b)
-                if (!done[b] && scp_solve_instance(*cta, *d, *p, b, io, s)) { done[b] = 1; --live; }
+            for (int b = 0; b < d->B; ++b) {
+                if (done[b]) continue;
+                if (poison) {
+                    for (auto &v : smem) v = NAN;
+                    for (auto &v : gmem) v = NAN;
+                }
+                if (scp_solve_instance(*cta, *d, *p, b, io, s)) { done[b] = 1; --live; }
+            }
         free(done);
         free(io.state);
     } else {

@@ -232,6 +232,25 @@ def test_scp_kernel_park_and_resume_is_bit_identical(oracle, quantum, monkeypatc
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
+@pytest.mark.parametrize("fname", ["circle8_hp10_step6.npz", "circle3_hp10_step8.npz"])
+def test_resumed_invocation_reads_nothing_left_over(oracle, fname, monkeypatch):
+    """A parked instance is resumed by whichever CTA pops it, in a working set that last served another instance.
+    With every invocation started from a working set full of NaNs (SCPB200_EMU_POISON) the results must still be those
+    of the uninterrupted run, bit for bit: nothing an invocation reads is left over from the one before."""
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    args = (S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], G["u_warm"][None], params_for(G))
+    monkeypatch.delenv("SCPB200_EMU_QUANTUM", raising=False)
+    monkeypatch.delenv("SCPB200_EMU_POISON", raising=False)
+    a = emu.scp_solve(*args)
+    monkeypatch.setenv("SCPB200_EMU_QUANTUM", "1")
+    monkeypatch.setenv("SCPB200_EMU_POISON", "1")
+    b = emu.scp_solve(*args)
+    assert not np.isnan(b["u"]).any()
+    for k in ("u", "traj", "U", "scp_iters", "ipm_iters", "status", "obj", "max_violation"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
 def test_plant_step_vs_reference_run(oracle):
     """Clamp + plant integration of main.py:104-109, 164-191 against the reference's own 50-step run: from the
     reference's measured state, actuated command and raw controller output of step i, the next measured state
