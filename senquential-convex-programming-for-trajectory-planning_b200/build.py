@@ -19,7 +19,9 @@ UNITS = [("scpb200.o", "scpb200.cu", []),
          ("scp_solve_generic.o", "scp_solve_generic.cu", []),
          ("scp_solve_v8h10_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=10", "-DSCP_FIXED_NT=256"]),
          ("scp_solve_v8h10_128.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=10", "-DSCP_FIXED_NT=128"]),
-         ("scp_solve_v8h20_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=256"])]
+         ("scp_solve_v8h20_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=256"]),
+         ("scp_solve_v8h20_512.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=512"]),
+         ("scp_solve_generic_wide.o", "scp_solve_generic.cu", ["-DSCP_GENERIC_WIDE"])]
 DEPS = ["scp_common.cuh", "ipm_core.cuh", "ops_pair.cuh", "ops_dense.cuh", "scp_kernels.cuh", "scp_solve_kernel.cuh",
         "scpb200.cu", "scp_solve_generic.cu", "scp_solve_fixed.cu", os.path.join("..", "..", "include", "scpb200.h")]
 

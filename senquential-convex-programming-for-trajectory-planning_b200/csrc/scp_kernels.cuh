@@ -596,10 +596,12 @@ SCP_HDFN ScpBump scp_bump(double *sh, size_t sh_lim, double *gl, bool all_shared
 
 // Vectors of the interior-point working set (small and hot first); the tile scratch and the normal matrix are
 // carved last by ipm_carve_big so that they are the first to overflow.
-SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc)
+// red_doubles: size of the per-warp reduction scratch of the kernel that will run on this layout (SCP_RED_DOUBLES of
+// ITS translation unit: units compiled for wider CTAs carry more warps)
+SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles = SCP_RED_DOUBLES)
 {
     m.n1 = n1; m.n1p = scp_round_up(n1, SCP_TILE); m.T = m.n1p / SCP_TILE; m.mc = mc;
-    m.red = bp.take(SCP_RED_DOUBLES);
+    m.red = bp.take((size_t)red_doubles);
     m.t8 = bp.take(16);
     m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
     m.dinv = bp.take(m.n1p);
@@ -643,10 +645,11 @@ struct ScpMem {
 // alpha_slots: pair-block mode of the normal matrix (> 0: tensor path, 0: entry by entry; see PairOp)
 // want_H: keep a shared-memory copy of the instance's cost blocks (read every iteration); otherwise they are read
 // from global memory.
-SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int alpha_slots, int want_H)
+SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int alpha_slots, int want_H,
+                        int red_doubles = SCP_RED_DOUBLES)
 {
     const int n = nVeh * Hp, mc = Hp * (nVeh * (nVeh - 1) / 2 + nVeh * nObst);
-    ipm_carve(bp, s.ipm, n + 1, mc);
+    ipm_carve(bp, s.ipm, n + 1, mc, red_doubles);
     s.g = bp.take((size_t)n * 2);
     s.dbar = bp.take((size_t)mc * 2);
     s.resp = bp.take((size_t)n * 2);
@@ -665,11 +668,11 @@ SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int
 
 // total doubles of the working set / split under a shared-memory limit (host-side planning)
 SCP_HDFN void scp_footprint(int nVeh, int Hp, int nObst, int alpha_slots, int want_H, size_t sh_lim, size_t *sh_used,
-                            size_t *gl_used)
+                            size_t *gl_used, int red_doubles = SCP_RED_DOUBLES)
 {
     ScpBump bp = scp_bump(0, sh_lim, 0, false);
     ScpMem s;
-    scp_carve(bp, s, nVeh, Hp, nObst, alpha_slots, want_H);
+    scp_carve(bp, s, nVeh, Hp, nObst, alpha_slots, want_H, red_doubles);
     *sh_used = bp.sh_off;
     *gl_used = bp.gl_off;
 }

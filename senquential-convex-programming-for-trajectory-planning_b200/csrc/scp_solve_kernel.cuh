@@ -45,6 +45,8 @@ struct ScpKernelEntry {
     int (*launch)(int grid, int threads, size_t smem_bytes, void *stream, const ScpKernelArgs *a);
     // tuning builds (-DSCP_PHASE_TIMERS): read and clear this unit's per-region cycle counters; null otherwise
     int (*read_timers)(unsigned long long *out32);
+    // CTA-width bound this unit was compiled for (SCP_MAX_THREADS of the unit): sizes the reduction scratch in the layout
+    int max_threads;
 };
 
 #if SCP_DEVICE_BUILD
@@ -73,7 +75,9 @@ __device__ __forceinline__ int queue_pop(const WorkQueue &q)
 // NVEH / HP / NT > 0: literal dimensions and CTA width.  After inlining the compiler folds every index computation
 // (n, n1, tile counts, divisions by Hp, strided loops over the CTA) into constants and unrolls the short loops; in
 // its generic form the kernel executes ~20 instructions of addressing and loop control per FP64 operation.
-template <bool ALL_SHARED, int NVEH, int HP, int NT>
+// MT = the unit's CTA-width bound: part of the kernel's NAME, so that the instantiations of units compiled for
+// different bounds (scp_solve_generic.cu, twice) are different symbols for the linker and the CUDA runtime.
+template <bool ALL_SHARED, int NVEH, int HP, int NT, int MT = SCP_MAX_THREADS>
 __global__ void __launch_bounds__(NT > 0 ? NT : SCP_MAX_THREADS, (NT > 0 && NT <= 128) ? 3 : (HP > 10 ? 1 : SCP_MIN_CTAS))
 k_scp_solve(const __grid_constant__ ScpKernelArgs a)
 {
@@ -139,7 +143,7 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
     SCP_ENTRY_TIMERS(NAME)                                                                             \
     extern "C" const ScpKernelEntry *NAME(void)                                                        \
     {                                                                                                  \
-        static const ScpKernelEntry e = {NAME##_prepare, NAME##_launch, SCP_ENTRY_TIMERS_PTR(NAME)};   \
+        static const ScpKernelEntry e = {NAME##_prepare, NAME##_launch, SCP_ENTRY_TIMERS_PTR(NAME), SCP_MAX_THREADS};    \
         return &e;                                                                                     \
     }
 #endif   // SCP_DEVICE_BUILD
@@ -150,3 +154,6 @@ extern "C" const ScpKernelEntry *scp_entry_generic_global(void);
 extern "C" const ScpKernelEntry *scp_entry_v8h10_t256(void);       // BASELINE.json configs[1]: 8 vehicles, Hp = 10
 extern "C" const ScpKernelEntry *scp_entry_v8h10_t128(void);
 extern "C" const ScpKernelEntry *scp_entry_v8h20_t256(void);       // BASELINE.json configs[2]: 8 vehicles, Hp = 20
+extern "C" const ScpKernelEntry *scp_entry_v8h20_t512(void);
+extern "C" const ScpKernelEntry *scp_entry_generic_shared_wide(void);   // run-time dimensions, CTAs of up to 512 threads
+extern "C" const ScpKernelEntry *scp_entry_generic_global_wide(void);

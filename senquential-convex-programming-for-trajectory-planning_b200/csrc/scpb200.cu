@@ -326,13 +326,13 @@ static size_t snap_bytes(const scpb200_dims *d)
 // Pick the occupancy target: the largest number of CTAs per SM (<= max_ctas) for which the whole working set is
 // shared-resident; if it does not fit even alone, one CTA per SM with the tail of the set in the global workspace.
 template <class KS, class KG, class FP>
-static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B, SolvePlan *pl)
+static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B, SolvePlan *pl, int max_threads = SCP_MAX_THREADS)
 {
     DevInfo di;
     int rc = dev_info(&di);
     if (rc) return rc;
-    if (pl->threads % 32 || pl->threads < 32 || pl->threads > SCP_MAX_THREADS)
-        return set_err(SCPB200_ERR_ARG, "SCPB200_THREADS must be a multiple of 32 in [32, SCP_MAX_THREADS]");
+    if (pl->threads % 32 || pl->threads < 32 || pl->threads > max_threads)
+        return set_err(SCPB200_ERR_ARG, "SCPB200_THREADS must be a multiple of 32 in [32, 256] (K4: [32, 512])");
     size_t shu = 0, glu = 0;
     const bool force_global = env_int("SCPB200_FORCE_GLOBAL_S", 0) != 0;
     int occ = 0;
@@ -388,7 +388,11 @@ static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
     if (rc) return rc;
     rc = plan_scp_threads(&big, 128, &narrow);
     if (rc) return rc;
-    const int threads = (narrow.all_shared && narrow.grid > wide.grid) ? 128 : 256;
+    int threads = (narrow.all_shared && narrow.grid > wide.grid) ? 128 : 256;
+    // Shapes that leave room for ONE CTA per SM (Hp >= 20 at 8 vehicles: the normal matrix alone is 118 KB; Hp = 50: it
+    // lives in the L2-resident workspace) are bound by the latency of their phases with 8 warps on the SM: 512-thread
+    // CTAs (128 registers per thread) take 37 % off a step at Hp = 50 and 3.5 % at Hp = 20 (profiles/r01_end_sweep_wide_ctas.txt).
+    if (threads == 256 && wide.ctas_per_sm == 1 && env_int("SCPB200_WIDE_CTAS", 1)) threads = 512;
     return plan_scp_threads(d, threads, pl);               // also leaves the function attributes of the chosen shape
 }
 
@@ -408,19 +412,25 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
     const int force_H = env_int("SCPB200_WANT_H", -1);             // tuning: -1 auto, 0 / 1 forced
     for (int want_H = 1; want_H >= 0; --want_H) {
         if (force_H >= 0 && want_H != force_H) continue;
-        auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu); };
-        SolvePlan cand = *pl;
+        // CTAs wider than 256 threads run the units compiled for them (16 warps of reduction scratch in the layout)
+        const bool wide = threads > 256;
+        const ScpKernelEntry *ks = wide ? scp_entry_generic_shared_wide() : scp_entry_generic_shared();
+        const ScpKernelEntry *kg = wide ? scp_entry_generic_global_wide() : scp_entry_generic_global();
         // the fixed-shape instantiations cover the layout without shared-resident cost blocks
-        const ScpKernelEntry *ks = scp_entry_generic_shared();
         if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && nObst == 0 && slots == 1) {
             if (Hp == 10 && threads == 256 && want_H == 0) ks = scp_entry_v8h10_t256();
             else if (Hp == 10 && threads == 128 && want_H == 0) ks = scp_entry_v8h10_t128();
             else if (Hp == 20 && threads == 256) ks = scp_entry_v8h20_t256();          // either placement of the cost blocks
+            else if (Hp == 20 && threads == 512) ks = scp_entry_v8h20_t512();
         }
-        int rc = plan_common(ks->prepare, scp_entry_generic_global()->prepare, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand);
+        const int red_doubles = 2 * SCP_RED_SLOTS * (ks->max_threads / 32);
+        if (kg->max_threads != ks->max_threads) return set_err(SCPB200_ERR_ARG, "internal: kernel units of one plan differ in CTA-width bound");
+        auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu, red_doubles); };
+        SolvePlan cand = *pl;
+        int rc = plan_common(ks->prepare, kg->prepare, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand, ks->max_threads);
         if (rc) return rc;
         cand.want_H = want_H;
-        cand.entry = cand.all_shared ? ks : scp_entry_generic_global();
+        cand.entry = cand.all_shared ? ks : kg;
         if (!have || (cand.all_shared && (!best.all_shared || cand.ctas_per_sm > best.ctas_per_sm))) { best = cand; have = 1; }
     }
     *pl = best;
@@ -433,6 +443,7 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
 static int plan_qp(int n1, int mc, int B, SolvePlan *pl)
 {
     pl->threads = env_int("SCPB200_THREADS", 256);
+    if (pl->threads > SCP_MAX_THREADS) pl->threads = SCP_MAX_THREADS;      // wider CTAs exist for K4 only
     pl->alpha_slots = 0;
     pl->want_H = 0;
     auto fp = [=](size_t lim, size_t *shu, size_t *glu) { ipm_footprint(n1, mc, lim, shu, glu); };

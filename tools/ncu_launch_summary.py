@@ -6,7 +6,7 @@ rows = [r for r in csv.reader(open(sys.argv[1], errors="replace")) if len(r) > 1
 agg = collections.OrderedDict()
 for r in rows:
     name = re.sub(r"^void ", "", r[4]).split("(")[0]
-    name = re.sub(r"<\(bool\)(\d), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", r"<\1,\2,\3,\4>", name)
+    name = re.sub(r"\((?:bool|int)\)", "", name)
     a = agg.setdefault(name, [0, 0.0, r[7], r[8]])
     a[0] += 1; a[1] += float(r[14]) * (1e-3 if r[13] == "ns" else 1.0)
 tot = sum(a[1] for a in agg.values())
