@@ -185,9 +185,12 @@ def workload_config(args, B_per_gpu, note=None):
 
 
 # ---------------------------------------------------------------------------------------------------- product arm
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, args=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture
-    summary (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that kernel was not captured."""
+    summary (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that kernel was not captured, or if
+    this run is not the default workload the captures were taken on (8 vehicles, Hp = 10, 1024 instances per GPU)."""
+    if args is not None and (args.nveh, args.hp, args.batch) != (8, 10, 1024):
+        return None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
@@ -328,7 +331,7 @@ def run_product(args):
         peaks, how = measured_peaks()
         abytes = assembly_bytes_per_qp(nVeh, Hp) * B
         asm = {"bound": "hbm", "kernel": "k_assemble", "achieved": abytes / (ams * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": ncu_traffic("k_assemble"),
+               "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": ncu_traffic("k_assemble", args),
                "peak_source": how,
                "ms_per_launch": ams, "algorithmic_bytes_per_launch": abytes}
         del outbuf
@@ -367,7 +370,7 @@ def run_product(args):
             "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe: DMMA m8n8k4 (the FP64 tensor path) and DFMA share one "
                          "peak on B200; the kernel is latency / issue bound far below it (DESIGN.md section 4)",
                          "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak, "traffic": ncu_traffic("k_scp_solve"),
+                         "frac": ach / fp64_peak, "traffic": ncu_traffic("k_scp_solve", args),
                          "peak_source": "measured on this pool's B200 (tools/microbench_dmma.cu: DMMA m8n8k4 37.0 TFLOP/s, "
                                         "DFMA 36.5; profiles/r01_microbench*.txt); MEASURED_PEAKS.json has no FP64 entry",
                          "algorithmic_flops_per_ipm_iteration": fit, "solve_share_of_step": float(solve_ms.sum() / step_ms.sum())},

@@ -720,10 +720,11 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
 // tuning builds only: read (and clear) the per-region cycle counters
 extern "C" int scpb200_debug_read_timers(unsigned long long *out32)
 {
-    const ScpKernelEntry *es[5] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
-                                   scp_entry_v8h10_t128(), scp_entry_v8h20_t256()};
+    const ScpKernelEntry *es[8] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
+                                   scp_entry_v8h10_t128(), scp_entry_v8h20_t256(), scp_entry_v8h20_t512(),
+                                   scp_entry_generic_shared_wide(), scp_entry_generic_global_wide()};
     for (int i = 0; i < 32; ++i) out32[i] = 0;
-    for (int e = 0; e < 5; ++e) {
+    for (int e = 0; e < 8; ++e) {
         unsigned long long part[32];
         if (!es[e]->read_timers || es[e]->read_timers(part)) return set_err(SCPB200_ERR_CUDA, "timer read failed");
         for (int i = 0; i < 32; ++i) out32[i] += part[i];

@@ -139,6 +139,26 @@ def test_dense_qp_kernel_vs_reference_solution(oracle, fname, reverse, force_glo
         assert viol <= 1e-6
 
 
+@pytest.mark.parametrize("nt,reverse,force_global", [(128, False, False), (256, True, True), (64, False, True)])
+def test_dense_qp_kernel_long_horizon_size(oracle, nt, reverse, force_global):
+    """A synthetic dense QP with 34 tile columns (n1 = 265; the golden Hp = 50 case, 51 columns, is too slow for the
+    emulator): tile tables beyond their precomputed range, normal matrix in the global workspace, three CTA widths."""
+    rng = np.random.default_rng(7)
+    n1, mc = 265, 30
+    M = rng.standard_normal((n1, n1)) / np.sqrt(n1)
+    P = M @ M.T + np.diag(rng.uniform(0.5, 2.0, n1))
+    q = rng.standard_normal(n1)
+    A = rng.standard_normal((mc, n1)) * (rng.uniform(size=(mc, n1)) < 0.3)
+    b = rng.uniform(0.1, 1.0, mc)
+    lb, ub = -np.full(n1, 0.4), np.full(n1, 0.4)
+    emu.config(nt=nt, reverse=reverse, force_global_S=force_global)
+    r = emu.qp_solve_dense(P[None], q[None], A[None], b[None], lb[None], ub[None], capi.default_params_py())
+    o = oracle.qp_boxed(P, q, A, b, lb, ub, opts=dict(abstol=1e-10, reltol=1e-10, feastol=1e-9))
+    assert o["status"] == 0 and (r["status"][0] & ~capi.ST_QP_DRES_FLOOR) == 0, (o["status"], r["status"][0])
+    assert np.abs(r["x"][0] - o["x"]).max() < 1e-7
+    assert (np.abs(o["x"]) > 0.399).sum() > 5            # the box is active somewhere: the scaled normal matrix is not benign
+
+
 @pytest.mark.parametrize("fname", FAST_FILES)
 def test_dense_and_structured_solvers_agree_with_oracle_iterations(oracle, fname):
     """The kernel's interior-point iteration follows coneqp: same iteration count (+-1) as the oracle run in
