@@ -1,8 +1,9 @@
 """Build libscpb200.so in-tree with nvcc for sm_100a (the only target).
 
-The library is five translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
-dimensions (scp_solve_generic.cu) and with the literal dimensions of the shapes BASELINE.json names (scp_solve_fixed.cu:
-8 vehicles x Hp 10 at two CTA widths, 8 vehicles x Hp 20) — compiled in parallel and linked into one shared object."""
+The library is seven translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
+dimensions (scp_solve_generic.cu, once for CTAs of up to 256 threads and once for up to 512) and with the literal
+dimensions of the shapes BASELINE.json names (scp_solve_fixed.cu: 8 vehicles x Hp 10 at two CTA widths, 8 vehicles x
+Hp 20 at two) — compiled in parallel and linked into one shared object."""
 from __future__ import annotations
 
 import os

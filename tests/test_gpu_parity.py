@@ -176,6 +176,38 @@ def test_scp_kernel_hp50_first_iteration(mods):
     assert abs(host(bs.log)[0, 0, 1] - G["SCP_ObjVal"][0]) <= 1e-6 * max(1.0, abs(G["SCP_ObjVal"][0]))
 
 
+def test_launch_shape_follows_dimensions_and_every_cta_width_agrees(mods, monkeypatch):
+    """The plan depends on the problem dimensions only: 3 x 128 threads per SM at Hp = 10, one 512-thread CTA where only
+    one fits (Hp = 20 shared-resident, Hp = 50 with the normal matrix in the workspace).  Forcing other CTA widths
+    (different kernel instantiations, different reduction order) gives the same solution to rounding."""
+    shapes = {"circle8_hp10_step6.npz": (128, True), "circle8_hp20_step5.npz": (512, True), "circle8_hp50_step3.npz": (512, False)}
+    for fname, (threads, shared) in shapes.items():
+        if not os.path.exists(os.path.join(GOLDEN, fname)):
+            continue
+        G = load_golden(fname)
+        nit = min(2, int(G["scp_iters"]))
+        sols = {}
+        for forced in (0, 128, 256, 512):
+            if forced:
+                monkeypatch.setenv("SCPB200_THREADS", str(forced))
+            else:
+                monkeypatch.delenv("SCPB200_THREADS", raising=False)
+            bs = make_batch(mods, G, B=nit, max_scp_iter=1)
+            bs.load_inputs(u=G["prev_u"][:nit])
+            pl = bs.plan()
+            if not forced:
+                assert (pl["threads"], bool(pl["S_in_shared"])) == (threads, shared), (fname, pl)
+            else:
+                assert pl["threads"] == forced
+            bs.controller_step()
+            sols[forced] = host(bs.u).copy()
+            for it in range(nit):
+                assert np.abs(sols[forced][it] - G["x"][it][:-1]).max() < 1e-6, (fname, forced, it)
+        for forced in (128, 256, 512):
+            assert np.abs(sols[forced] - sols[0]).max() < 1e-7, (fname, forced)
+    monkeypatch.delenv("SCPB200_THREADS", raising=False)
+
+
 @pytest.mark.parametrize("fname", NOT50)
 def test_scp_kernel_free_running(mods, fname):
     G = load_golden(fname)
