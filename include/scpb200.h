@@ -47,6 +47,9 @@ extern "C" {
                                      * residual within tolerance, dual residual within 100 qp_feastol and no longer
                                      * decreasing (further iterations only degrade it) */
 
+#define SCPB200_ST_QP_WARM_RESTART 64 /* log rows only: the QP's warm start did not converge within qp_warm_max_iter and it
+                                     * was solved again from the cold starting point (the row's iteration count is the sum) */
+
 typedef struct scpb200_dims {
     int32_t B;      /* instances (independent scenarios / noise samples) */
     int32_t nVeh;   /* vehicles per instance (Scenarios.py:59) */
@@ -89,6 +92,20 @@ typedef struct scpb200_params {
     int32_t qp_dres_floor_factor; /* a QP whose gap and primal residual have converged is accepted when its dual residual is
                               * within this factor of qp_feastol and no longer decreasing (SCPB200_ST_QP_DRES_FLOOR);
                               * 0 = never (iterate to ipm_max_iter).  Default 100. */
+    /* extension: steering-rate rows inside the QP (the reference only clamps AFTER the solve, main.py:144-174).
+     * With enable_rate_rows = 1 every QP carries, per vehicle v and step k, the two rows
+     *     u_v[k] - u_v[k-1] <= duLim,   u_v[k-1] - u_v[k] <= duLim        (u_v[-1] = u_prev[v], the command being actuated)
+     * appended after the collision / obstacle rows in the order (v, k, +), (v, k, -): mc grows by 2 nVeh Hp.
+     * Default 0 reproduces the reference bit for bit. */
+    int32_t enable_rate_rows;
+    int32_t log_capacity;    /* rows per instance allocated in the `log` array of scpb200_scp_solve (0: max_scp_iter rows);
+                              * a call with max_scp_iter > log_capacity > 0 is rejected instead of writing past the rows */
+    double duLim;            /* steering-rate bound per MPC step, Scenarios.py:54 (6 deg); read when enable_rate_rows = 1 */
+    uint32_t noise_stream;   /* scpb200_ode_predict only: which of its callers draws (0 = the delay-compensation prediction,
+                              * 1 = tick-path predictions, ...).  The set-up, the plant step and every ode_predict caller use
+                              * disjoint Philox streams, so that the draws of one MPC step are independent as the reference's
+                              * np.random.normal draws are (Model.py:84-86). */
+    uint32_t reserved0;
 } scpb200_params;
 
 /* width of one row of the per-iteration log of scpb200_scp_solve (SCP_controller.py:169-189, scalar fields) */
@@ -164,6 +181,15 @@ int scpb200_forward_u(const scpb200_dims *d, const double *g, const double *cter
  */
 int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *p, const double *x, const double *u_ref,
                         const double *veh, double T, int32_t steps, int32_t nsub, double *out, void *stream);
+
+/*
+ * Test / validation entry: the raw N(0,1) pairs the kernels consume (Philox4x32-10 keyed by seed; counter words
+ * instance0 + b, vehicle, counter0 + c, stream tag; Box-Muller).  out[B,nVeh,ncount,2].  Replaces nothing in the
+ * reference (np.random.normal, Model.py:84-86, cannot be reproduced in a batched kernel); it exists so that the
+ * generator can be checked against Random123's known-answer vectors and statistically (hard part 7).
+ */
+int scpb200_noise_draws(const scpb200_dims *d, const scpb200_params *p, uint32_t noise_stream, uint32_t counter0,
+                        int32_t ncount, double *out, void *stream);
 
 /*
  * The caller's half of one MPC step — replaces main.py:104-109 (dynamic steering limit),

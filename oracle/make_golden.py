@@ -39,6 +39,7 @@ import oracle  # noqa: E402
 import cvxpy as cp_stub  # noqa: E402  (the capture stub)
 
 QP_ITERS = []
+QP_MULT = []           # per QP, in solve order: the multipliers (zA, zub, zlb) of the extended-precision solution
 
 
 #: the QP "truth": the interior-point iteration run in __float128 down to 1e-13 (see scp_oracle.c, a8)
@@ -49,6 +50,7 @@ def _solver(P, q, A, b, lb, ub):
     r = oracle.qp_boxed(P, q, A, b, lb, ub, opts=QUAD_TOL, inf_bound=1e20, quad=True)
     assert r["status"] == 0, {k: v for k, v in r.items() if np.ndim(v) == 0}
     QP_ITERS.append(r["iterations"])
+    QP_MULT.append((r["zA"].copy(), r["zub"].copy(), r["zlb"].copy()))
     return r["x"]
 
 
@@ -103,6 +105,7 @@ def frog_scenario(Hp):
 def run(nveh, radius, Hp, nsim, frog=False):
     ITER_INPUTS.clear()
     QP_ITERS.clear()
+    QP_MULT.clear()
     cp_stub.CAPTURE.clear()
     sc = frog_scenario(Hp) if frog else circle_scenario(nveh, radius, Hp)
     sim = ref_main.Simulation(sc, doOnlinePlot=False, isNoise=False)
@@ -164,6 +167,13 @@ def step_record(sim, i, dense_iters):
         delta=np.array([float(np.ravel(v)[0]) for v in log["delta"]]),
         feasible=np.array([bool(v) for v in log["feasible"]]),
     )
+    # multipliers of every QP of this step (solve order = step order): the inputs of the independent KKT certificate in
+    # tests/test_qp_certificates.py (stationarity / primal / dual sign / complementarity in NumPy longdouble)
+    off = sum(len(o["optimization_log"]["x"]) for o in sim.controllerOutputs[:i])
+    assert len(QP_MULT) >= off + nit
+    rec["zA"] = np.array([QP_MULT[off + it][0] for it in range(nit)])
+    rec["zub"] = np.array([QP_MULT[off + it][1] for it in range(nit)])
+    rec["zlb"] = np.array([QP_MULT[off + it][2] for it in range(nit)])
     # the warm start the reference actually linearised about in iteration 0 (after the eps tweak of :75-76)
     for it in dense_iters:
         if it < 0:
@@ -205,7 +215,7 @@ def collect(nveh, radius, Hp, nsim, steps, dense_iters, tag, full_run=False, fro
         rec.update({f"sc_{k}": v for k, v in const.items()})
         path = os.path.join(OUT, f"{tag}_step{i}.npz")
         np.savez_compressed(path, **rec)
-        print(f"    wrote {os.path.relpath(path, ROOT)} ({os.path.getsize(path) / 1024:.0f} KiB, "
+        print(f"    wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB, "
               f"{rec['scp_iters']} SCP iterations)")
     if full_run:
         nsteps = sc.Nsim
@@ -248,7 +258,11 @@ def collect(nveh, radius, Hp, nsim, steps, dense_iters, tag, full_run=False, fro
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
+    ap.add_argument("--out", default=None, help="write the fixtures here instead of tests/golden (regeneration checks)")
     args = ap.parse_args()
+    global OUT
+    if args.out:
+        OUT = os.path.abspath(args.out)
     os.makedirs(OUT, exist_ok=True)
     if args.only in (None, "hp10"):
         collect(8, 30, 10, None, [0, 6, 10, 29], [0, -1], "circle8_hp10", full_run=True)

@@ -71,6 +71,7 @@ class IterClass:
         eng = engine_for(scenario)
         eng.params.noise_counter = int(getattr(scenario, "_iter_counter", 0))
         scenario._iter_counter = eng.params.noise_counter + 1
+        self._noise_counter = eng.params.noise_counter
         xm = torch.as_tensor(np.ascontiguousarray(x_measured, dtype=float).reshape(1, nVeh, nx), device=eng.device)
         ur = torch.as_tensor(np.ascontiguousarray(u_path[:, -1], dtype=float).reshape(1, nVeh), device=eng.device)
         Y = eng.ode_predict(xm, ur, float(T), steps=steps, nsub=16)                        # [1,nVeh,steps,6]

@@ -36,8 +36,29 @@ class SCPcontroller:
         self.scenario_uLim = getattr(scenario, "uLim", scenario.mechanicalSteeringLimit)     # SCP_controller.py:34, SURVEY F1
         self.mpc = MPCclass(scenario, Iter)            # K1 on device (or the set-up IterClass already ran)
         self._eng = self.mpc._engine
+        self._setup_id = Iter._setup_id                # the engine state this controller's problem data belong to
         self.qcqp = self.QCQP_formulate(scenario)
         self.u = np.zeros([self.nVeh * self.Hp, 1])
+
+    def _engine(self):
+        """The engine (one set of device buffers per problem shape) is shared between every Iter / controller of that
+        shape.  If another IterClass / MPCclass has used it since this controller was built, its buffers hold the other
+        problem's data: reload this controller's problem (scenario constants, x0, u0, obstacles) and re-run K1.  The
+        reference's objects are self-contained; this keeps that property."""
+        eng = self._eng
+        if getattr(eng, "_setup_serial", None) != self._setup_id:
+            from .MPC_Iter import engine_for, _snapshot_id
+            eng = engine_for(self.scenario)
+            nVeh = self.nVeh
+            eng.load_inputs(x0=np.asarray(self.Iter.x0, float)[None], u0=np.asarray(self.Iter.u0, float).reshape(1, nVeh))
+            if self.nObst:
+                eng.load_inputs(obst=np.transpose(np.asarray(self.Iter.obstacleFutureTrajectories, float), (0, 2, 1))[None])
+            eng.params.noise_counter = int(getattr(self.Iter, "_noise_counter", 0))
+            eng.setup()
+            self._eng = eng
+            self._setup_id = self.Iter._setup_id = _snapshot_id(eng)
+            self.Iter._engine = eng
+        return eng
 
     # ---------------------------------------------------------------------------------------------- the controller
     def SCP_controller(self, Iter):
@@ -68,7 +89,7 @@ class SCPcontroller:
         the scalar fields of the reference's log (dense P / Aineq per iteration are available on demand through
         BatchSCP.assemble_dense)."""
         import torch
-        eng = self._eng
+        eng = self._engine()
         if abs(u_approx[0, 0]) < np.spacing(1):
             u_approx[0] = np.spacing(1)                 # :75-76 (mutates the caller's array, as the reference does)
         eng.load_inputs(u=np.ascontiguousarray(u_approx, dtype=float).reshape(1, -1))
@@ -94,7 +115,7 @@ class SCPcontroller:
     def forward_U(self, u):
         """SCP_controller.py:199-213: Traj[Hp,ny,nVeh], U[Hp,nu,nVeh]."""
         import torch
-        eng = self._eng
+        eng = self._engine()
         ut = torch.as_tensor(np.ascontiguousarray(u, dtype=float).reshape(1, -1), device=eng.device)
         traj, U = eng.forward_u(ut)
         return traj[0].cpu().numpy(), U[0].cpu().numpy()[:, None, :]
@@ -103,7 +124,7 @@ class SCPcontroller:
         """SCP_controller.py:215-265.  Items 3-4 of the reference's tuple (a penalty score and its gradient that no
         caller reads) are returned as None."""
         import torch
-        eng = self._eng
+        eng = self._engine()
         ut = torch.as_tensor(np.ascontiguousarray(U, dtype=float).reshape(1, -1), device=eng.device)
         ev = eng.evaluate(ut, want_ci=True)
         ci = ev["ci"][0].cpu().numpy()

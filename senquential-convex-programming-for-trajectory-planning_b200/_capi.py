@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("SCPB200_LIB") or os.path.join(HERE, "libscpb200.so") 
 
 LOG_W = 10
 ST_QP_MAXITER, ST_QP_PIVOT, ST_SCP_MAXITER, ST_INFEASIBLE, ST_SETUP, ST_QP_DRES_FLOOR = 1, 2, 4, 8, 16, 32
+ST_QP_WARM_RESTART = 64          # log rows only
 
 
 class Dims(C.Structure):
@@ -31,6 +32,8 @@ class Params(C.Structure):
         ("instance0", C.c_uint32), ("noise_counter", C.c_uint32),
         ("qp_warm_relgap", C.c_double), ("qp_warm_max_iter", C.c_int32), ("qp_warm_min_iter", C.c_int32),
         ("qp_warm_carry", C.c_int32), ("qp_dres_floor_factor", C.c_int32),
+        ("enable_rate_rows", C.c_int32), ("log_capacity", C.c_int32), ("duLim", C.c_double),
+        ("noise_stream", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -45,6 +48,7 @@ def default_params_py() -> Params:
     p.ipm_max_iter, p.trust_radius, p.noise_sigma, p.seed, p.instance0, p.noise_counter = 60, 1e308, 0.0, 0, 0, 0
     p.qp_warm_start, p.qp_warm_relgap, p.qp_warm_max_iter, p.qp_warm_min_iter, p.qp_warm_carry = 1, 1.0, 30, 5, 0
     p.qp_dres_floor_factor = 100
+    p.enable_rate_rows, p.log_capacity, p.duLim = 0, 0, math.pi / 180.0 * 6.0
     return p
 
 
@@ -64,6 +68,7 @@ PROTOTYPES = {
     "scpb200_qcqp_evaluate": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 16,
     "scpb200_forward_u": [C.POINTER(Dims)] + [_P] * 6,
     "scpb200_ode_predict": [C.POINTER(Dims), C.POINTER(Params), _P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P, _P],
+    "scpb200_noise_draws": [C.POINTER(Dims), C.POINTER(Params), C.c_uint32, C.c_uint32, C.c_int32, _P, _P],
     "scpb200_plant_step": [C.POINTER(Dims), C.POINTER(Params), _P, _P, C.c_double, C.c_double, C.c_double, C.c_double,
                            C.c_int32, _P, _P, _P, _P, _P],
     "scpb200_advance_linear": [C.POINTER(Dims), _P, _P, C.c_double, C.c_double, _P, _P, _P],

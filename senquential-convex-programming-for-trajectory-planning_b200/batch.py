@@ -75,7 +75,8 @@ class BatchSCP:
             self.u = torch.zeros(B_, self.n, **f64)
             self.traj = torch.zeros(B_, Hp_, 2, V, **f64)
             self.U = torch.zeros(B_, Hp_, V, **f64)
-            self.log = torch.zeros(B_, self.params.max_scp_iter, _capi.LOG_W, **f64) if keep_log else None
+            self.log = None
+            self._size_log()
             self.scp_iters = torch.zeros(B_, **i32)
             self.ipm_iters = torch.zeros(B_, **i32)
             self.status = torch.zeros(B_, **i32)
@@ -92,6 +93,19 @@ class BatchSCP:
         self._have_work = False
 
     # ------------------------------------------------------------------------------------------------ plumbing
+    def _size_log(self):
+        """The per-iteration log holds `log_capacity` rows per instance; the kernel indexes it with that stride and the
+        C entry rejects max_scp_iter > log_capacity.  Raising params.max_scp_iter after construction (the facade does,
+        per scenario) therefore reallocates here instead of writing past the rows."""
+        if not self.keep_log:
+            self.params.log_capacity = 0
+            return
+        need = int(self.params.max_scp_iter)
+        if self.log is None or self.log.shape[1] < need:
+            with torch.cuda.device(self.device):
+                self.log = torch.zeros(self.B, max(need, 1), _capi.LOG_W, dtype=torch.float64, device=self.device)
+        self.params.log_capacity = int(self.log.shape[1])
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -127,6 +141,7 @@ class BatchSCP:
 
     def solve(self):
         """K4: SCPcontroller.SCP_controller (SCP_controller.py:40-197) for the whole batch; u is warm start and result."""
+        self._size_log()
         with torch.cuda.device(self.device):
             order = None
             if self.schedule_by_previous_work and self._have_work and self.B > 1:

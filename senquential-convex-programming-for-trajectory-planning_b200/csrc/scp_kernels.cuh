@@ -23,10 +23,17 @@ SCP_HDFN void scp_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-SCP_HDFN void scp_noise_pair(uint64_t seed, uint32_t instance, uint32_t vehicle, uint32_t counter, double out[2])
+// Every consumer of noise inside one MPC step draws from its OWN stream (the fourth counter word): the set-up (K1),
+// the plant step, the delay-compensation prediction and the tick-path predictions all run with the same
+// noise_counter (the MPC step index), and the reference's np.random.normal draws are independent between them.
+#define SCP_NOISE_SETUP 0u      /* K1: Ec = f(x,u) + noise - ... (Model.py:58 through :84-86) */
+#define SCP_NOISE_PLANT 1u      /* plant integration, main.py:185-190 */
+#define SCP_NOISE_ODE 2u        /* scpb200_ode_predict: 2 + params.noise_stream (0 = delay compensation, MPC_Iter.py:25-33) */
+SCP_HDFN void scp_noise_pair(uint64_t seed, uint32_t instance, uint32_t vehicle, uint32_t counter, double out[2],
+                             uint32_t stream = SCP_NOISE_SETUP)
 {
     uint32_t r[4];
-    scp_philox4x32_10(instance, vehicle, counter, 0x5C9B200u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    scp_philox4x32_10(instance, vehicle, counter, 0x5C9B200u + stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     const double u1 = ((double)(((uint64_t)r[0] << 21) ^ (r[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
     const double u2 = (double)(((uint64_t)r[2] << 21) ^ (r[3] >> 11)) * (1.0 / 9007199254740992.0);
     const double rad = sqrt(-2.0 * log(u1)), ang = 6.283185307179586476925286766559 * u2;
@@ -340,10 +347,10 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
 // interval, writing `steps` samples (t = 0 .. T inclusive) — the delay-compensation prediction of IterClass
 // (MPC_Iter.py:25-33: odeint over linspace(0, delay_x+dt+delay_u, 10)).  With noise_sigma > 0 every RHS
 // evaluation adds N(0, sigma) to (dx, dy) (Model.py:84-86) from the keyed Philox stream
-// (counter = noise_counter * 65536 + stage index).
+// (counter = noise_counter * 65536 + stage index, stream = the consumer's tag, see scp_noise_pair).
 SCP_HDFN void scp_ode_predict_vehicle(const double *x_in, double u_ref, double Lf, double Lr, double T, int steps,
                                       int nsub, double noise_sigma, uint64_t seed, uint32_t instance, uint32_t vehicle,
-                                      uint32_t noise_counter, double *out /*[steps][6]*/)
+                                      uint32_t noise_counter, double *out /*[steps][6]*/, uint32_t noise_stream = SCP_NOISE_ODE)
 {
     double x[6], k1[6], k2[6], k3[6], k4[6], xt[6];
     for (int i = 0; i < 6; ++i) { x[i] = x_in[i]; out[i] = x_in[i]; }
@@ -355,7 +362,7 @@ SCP_HDFN void scp_ode_predict_vehicle(const double *x_in, double u_ref, double L
 #define SCP_RHS(xx, kk)                                                                         \
     scp_bicycle_rhs(xx, u_ref, Lf, Lr, kk);                                                     \
     if (noise_sigma > 0.0) {                                                                    \
-        scp_noise_pair(seed, instance, vehicle, noise_counter * 65536u + (stage++), nz);        \
+        scp_noise_pair(seed, instance, vehicle, noise_counter * 65536u + (stage++), nz, noise_stream); \
         kk[0] += noise_sigma * nz[0];                                                           \
         kk[1] += noise_sigma * nz[1];                                                           \
     }
@@ -401,7 +408,7 @@ SCP_HDFN void scp_plant_step_vehicle(double *x, double *u_act, const double *U, 
         prev = uj;
     }
     double out[12];
-    scp_ode_predict_vehicle(x, u0, Lf, Lr, T, 2, nsub, noise_sigma, seed, instance, vehicle, noise_counter, out);
+    scp_ode_predict_vehicle(x, u0, Lf, Lr, T, 2, nsub, noise_sigma, seed, instance, vehicle, noise_counter, out, SCP_NOISE_PLANT);
     for (int i = 0; i < 6; ++i) x[i] = out[6 + i];
     *u_act = first;
     if (uMax_out) *uMax_out = uMax;
@@ -800,6 +807,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             }
         CTA_PHASE_END
         IpmResult res;
+        int warm_iters = 0;                                 // iterations of an abandoned warm attempt (logged with the QP)
         ctl.warm = ctl.snap && snap_valid;
         if (ctl.warm) {
             // a warm start that does not converge quickly (the active set moved too far) is abandoned for a cold one
@@ -807,7 +815,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             ctl.max_iter = p.qp_warm_max_iter > 0 ? p.qp_warm_max_iter : cap;
             ipm_solve(cta, op, m, ctl, &res);
             ctl.max_iter = cap;
-            if (res.status & SCPB200_ST_QP_MAXITER) { ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
+            if (res.status & SCPB200_ST_QP_MAXITER) { warm_iters = res.iters; ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
         } else {
             ipm_solve(cta, op, m, ctl, &res);
         }
@@ -833,9 +841,12 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         if (io.log) {
             CTA_PHASE(tid)
                 if (tid == 0) {
-                    double *L = io.log + ((size_t)b * p.max_scp_iter + it) * SCPB200_LOG_W;
+                    const int log_rows = p.log_capacity > 0 ? p.log_capacity : p.max_scp_iter;     // rows per instance
+                    double *L = io.log + ((size_t)b * log_rows + it) * SCPB200_LOG_W;
                     L[0] = slack; L[1] = fval; L[2] = ev.obj; L[3] = delta_hat; L[4] = delta; L[5] = ev.feasible;
-                    L[6] = ev.max_violation; L[7] = ev.sum_violations; L[8] = res.iters; L[9] = res.status;
+                    L[6] = ev.max_violation; L[7] = ev.sum_violations;
+                    L[8] = res.iters + warm_iters;          // sum over the log = ipm_iters[b]
+                    L[9] = res.status | (warm_iters ? SCPB200_ST_QP_WARM_RESTART : 0);
 #ifdef SCP_DIAG_LOG     /* tuning builds: where did the interior-point method stop */
                     L[5] = res.dres; L[6] = res.pres; L[7] = res.relgap; L[3] = res.gap;
 #endif

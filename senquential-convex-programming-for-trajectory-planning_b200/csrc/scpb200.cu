@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "scp_solve_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -53,6 +55,10 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->qp_warm_min_iter = 5;
     p->qp_warm_carry = 0;
     p->qp_dres_floor_factor = 100;
+    p->enable_rate_rows = 0;
+    p->log_capacity = 0;
+    p->duLim = 3.14159265358979323846 / 180.0 * 6.0;  /* Scenarios.py:54 */
+    p->noise_stream = 0;
 }
 
 extern "C" int scpb200_device_count(void)
@@ -178,7 +184,21 @@ __global__ void __launch_bounds__(128) k_ode_predict(scpb200_dims d, scpb200_par
         const int b = e / d.nVeh, v = e - b * d.nVeh;
         scp_ode_predict_vehicle(x + (size_t)e * 6, u_ref[e], veh[(size_t)e * 5], veh[(size_t)e * 5 + 1], T, steps, nsub,
                                 p.noise_sigma, p.seed, p.instance0 + (uint32_t)b, (uint32_t)v, p.noise_counter,
-                                out + (size_t)e * steps * 6);
+                                out + (size_t)e * steps * 6, SCP_NOISE_ODE + p.noise_stream);
+    }
+}
+
+// raw draws of the keyed generator (test entry: known-answer and statistical checks of what the kernels consume)
+__global__ void __launch_bounds__(128) k_noise_draws(scpb200_dims d, scpb200_params p, uint32_t stream, uint32_t counter0,
+                                                     int ncount, double *out)
+{
+    const size_t tot = (size_t)d.B * d.nVeh * ncount;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(e % ncount), v = (uint32_t)((e / ncount) % d.nVeh), b = (uint32_t)(e / ncount / d.nVeh);
+        double nz[2];
+        scp_noise_pair(p.seed, p.instance0 + b, v, counter0 + c, nz, stream);
+        out[e * 2] = nz[0];
+        out[e * 2 + 1] = nz[1];
     }
 }
 
@@ -369,6 +389,8 @@ static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B
 }
 
 static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
+// rate rows change the working-set layout (mc grows by 2n): part of the plan key, set by the entry points before planning
+static thread_local int g_plan_rate_rows = 0;
 
 // Launch shape.  A 128-thread CTA runs an interior-point iteration only ~7 % slower than a 256-thread one (the
 // iteration is a chain of short dependent phases), and three of them fit an SM where the register file holds two
@@ -377,7 +399,7 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
 // chosen from the problem dimensions alone, never from the batch size: the CTA width fixes the order of the
 // reductions, and per-instance results must not depend on how a batch is sharded.
 // SCPB200_THREADS overrides (tuning).
-static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
+static int plan_scp_uncached(const scpb200_dims *d, SolvePlan *pl)
 {
     const int forced = env_int("SCPB200_THREADS", 0);
     if (forced > 0) return plan_scp_threads(d, forced, pl);
@@ -394,6 +416,53 @@ static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
     // CTAs (128 registers per thread) take 37 % off a step at Hp = 50 and 3.5 % at Hp = 20 (profiles/r01_end_sweep_wide_ctas.txt).
     if (threads == 256 && wide.ctas_per_sm == 1 && env_int("SCPB200_WIDE_CTAS", 1)) threads = 512;
     return plan_scp_threads(d, threads, pl);               // also leaves the function attributes of the chosen shape
+}
+
+// The plan is a pure function of (device, nVeh, Hp, nObst, rate rows, tuning environment) up to the clipping of the grid
+// by the batch size; planning costs three passes of attribute updates and occupancy queries, so it is done once per key
+// and every later call (one per MPC step) only clips the grid.
+struct PlanKey {
+    int dev, nVeh, Hp, nObst, rate, env[9];
+    bool operator==(const PlanKey &o) const { return memcmp(this, &o, sizeof *this) == 0; }
+};
+struct PlanSlot {
+    PlanKey key;
+    SolvePlan plan;
+};
+#define PLAN_CACHE_SLOTS 32
+static PlanSlot g_plan_cache[PLAN_CACHE_SLOTS];
+static int g_plan_count = 0;
+static std::mutex g_plan_mutex;
+
+static int plan_scp(const scpb200_dims *d, SolvePlan *pl)
+{
+    PlanKey key;
+    memset(&key, 0, sizeof key);
+    CUDA_TRY(cudaGetDevice(&key.dev));
+    key.nVeh = d->nVeh; key.Hp = d->Hp; key.nObst = d->nObst; key.rate = g_plan_rate_rows;
+    const char *names[9] = {"SCPB200_THREADS", "SCPB200_WIDE_CTAS", "SCPB200_ALPHA_SLOTS", "SCPB200_WANT_H", "SCPB200_SPECIALISE",
+                            "SCPB200_MAX_CTAS", "SCPB200_CTAS_PER_SM", "SCPB200_FORCE_GLOBAL_S", "SCPB200_LEGACY_SOLVER"};
+    for (int i = 0; i < 9; ++i) key.env[i] = env_int(names[i], -12345);
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    int hit = -1;
+    for (int i = 0; i < g_plan_count; ++i)
+        if (g_plan_cache[i].key == key) { hit = i; break; }
+    if (hit < 0) {
+        scpb200_dims big = *d;
+        big.B = 1 << 30;
+        SolvePlan full;
+        int rc = plan_scp_uncached(&big, &full);
+        if (rc) return rc;
+        hit = g_plan_count < PLAN_CACHE_SLOTS ? g_plan_count++ : 0;
+        g_plan_cache[hit].key = key;
+        g_plan_cache[hit].plan = full;
+    }
+    *pl = g_plan_cache[hit].plan;
+    long grid = pl->grid;
+    if (grid > d->B) grid = d->B;
+    if (grid < 1) grid = 1;
+    pl->grid = (int)grid;
+    return 0;
 }
 
 static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
@@ -599,6 +668,18 @@ extern "C" int scpb200_ode_predict(const scpb200_dims *d, const scpb200_params *
     return 0;
 }
 
+extern "C" int scpb200_noise_draws(const scpb200_dims *d, const scpb200_params *p, uint32_t noise_stream, uint32_t counter0,
+                                   int32_t ncount, double *out, void *stream)
+{
+    if (!d || !p || !out || d->B < 0 || d->nVeh < 1 || ncount < 1) return set_err(SCPB200_ERR_ARG, "scpb200_noise_draws: bad argument");
+    if (d->B == 0) return 0;
+    const size_t tot = (size_t)d->B * d->nVeh * ncount;
+    const int grid = (int)((tot + 127) / 128 < 148 * 16 ? (tot + 127) / 128 : 148 * 16);
+    k_noise_draws<<<grid, 128, 0, (cudaStream_t)stream>>>(*d, *p, noise_stream, counter0, ncount, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int scpb200_plant_step(const scpb200_dims *d, const scpb200_params *p, const double *veh, const double *U,
                                   double mech_limit, double lat_acc_limit, double duLim, double T, int32_t nsub,
                                   double *x_meas, double *u_act, double *u_max_out, double *U_clamped, void *stream)
@@ -687,6 +768,8 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
         return set_err(SCPB200_ERR_ARG, "scpb200_scp_solve: NULL argument");
     if (d->nObst && (!dsafe_obst || !obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
     if (p->max_scp_iter < 1) return set_err(SCPB200_ERR_ARG, "max_scp_iter must be >= 1");
+    if (log && p->log_capacity > 0 && p->max_scp_iter > p->log_capacity)
+        return set_err(SCPB200_ERR_ARG, "scpb200_scp_solve: max_scp_iter exceeds log_capacity (rows allocated per instance in log)");
     if (d->B == 0) return 0;
     SolvePlan pl;
     rc = plan_scp(d, &pl);

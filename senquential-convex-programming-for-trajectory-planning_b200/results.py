@@ -102,11 +102,15 @@ class BatchRollout:
         ev[2].record()
         # tick-resolution plant path of this step, sampled before the state is advanced
         u_prev = self.u_act.clone()
+        # (each ode_predict caller draws from its own Philox stream: 0 delay compensation, 1 / 2 the tick paths)
+        bs.params.noise_stream = 1
         ticks = bs.ode_predict(self.x, u_prev, self.dt, steps=tps + 1, nsub=4)             # [B,nVeh,tps+1,6]
         if self.tdu > 1:
             older = self._u_older if i > 0 else self._u_init
+            bs.params.noise_stream = 2
             early = bs.ode_predict(self.x, older, (self.tdu - 1) * self.tick, steps=self.tdu, nsub=4)
             ticks[:, :, 1:self.tdu, :] = early[:, :, 1:, :]
+        bs.params.noise_stream = 0
         self._u_older = u_prev
         _, self._U_clamped = bs.plant_step(self.x, self.u_act, self.mech, self.lat, self.duLim, want_clamped=True)
         ticks[:, :, tps, :] = self.x                                                        # the state the next step measures
