@@ -14,8 +14,8 @@
 // |value| >= inf_bound (the omega <= 1e25 row of SCP_controller.py:127) are treated as absent.
 //
 // The normal matrix S lives as a tile-packed lower triangle (8x8 tiles, layout scp_tphys) and is factorised by a
-// blocked right-looking Cholesky whose factor is then inverted in place (chol_tiles), so that every solve is two
-// triangular mat-vecs.
+// blocked right-looking Cholesky (chol_factor); the diagonal tiles of the factor are then inverted in place
+// (chol_invert_diag) and every solve is a tile-wise substitution inside one warp (chol_solve).
 //
 // The constraint operator `Op` supplies the problem-specific pieces (structured pair rows for the fused SCP
 // kernel, dense rows for the CVXOPT-replacement entry).  Products with A and A' are split into a CTA-wide
@@ -51,13 +51,12 @@ struct IpmCtl {
 struct IpmMem {
     int n1, n1p, T, mc;
     double *S;      // [T(T+1)/2 * 64]   tile-packed lower triangle of the normal matrix / its Cholesky factor;
-                    //                   chol_tiles leaves X = L^-1 here
+                    //                   (diagonal tiles replaced by their inverses after chol_invert_diag)
     double *x, *q, *rx, *dx, *tn;                    // [n1p]
     double *bA, *sA, *zA, *rzA, *dsA, *dzA, *ccA, *eA;   // [mc]    collision rows (e = 1/(s + delta z))
     double *ub, *sU, *zU, *dsU, *dzU, *ccU, *eU;         // [n1p]   x <= ub rows
     double *lb, *sL, *zL, *dsL, *dzL, *ccL, *eL;         // [n1p]   x >= lb rows
     double *dinv;   // [n1p]             reciprocal pivots of the factor
-    double *wbuf;   // [max(T*64, 4*n1p)] tile scratch of the inversion sweep / partial sums of the solves
     double *red;    // [SCP_RED_DOUBLES] reduction scratch (double-buffered, see scp_common.cuh)
     double *t8;     // [16] tile-solve scratch (8) + flags
 };
@@ -67,6 +66,10 @@ struct IpmResult {
     int iters, status;
     int snap_saved;      // an iterate was written to ctl.snap during this solve
 };
+
+// Padded order of the normal matrix: a multiple of the tile size with AT LEAST ONE padding row.  The last row
+// (n1p - 1) carries a right-hand side through the factorisation (see chol_factor).
+SCP_HDFN int ipm_padded(int n1) { return scp_round_up(n1 + 1, SCP_TILE); }
 
 SCP_HDFN size_t ipm_snap_doubles(int n1p, int mc) { return (size_t)5 * n1p + 2 * (size_t)((mc + 1) & ~1); }
 
@@ -222,71 +225,22 @@ SCP_FN void warp_tile_syrk2(int lane, double *C, const double *A, const double *
 #endif
 }
 
-// out = sign * sum_{j < nprod} A_j B_j   with A_j = Abase + j*astride, B_j = Bbase + j*bstride (plain products)
-SCP_FN void warp_tile_gemm_sum(int lane, double *out, const double *Abase, int astride, const double *Bbase, int bstride,
-                               int nprod, double sign)
-{
-#if SCP_DEVICE_BUILD
-    // two accumulator pairs (even / odd products): the DMMA chain of one tile would otherwise be 2 * nprod deep
-    double n0 = 0.0, n1 = 0.0, m0 = 0.0, m1 = 0.0;
-    const int ia0 = scp_frag_rowmajor(lane, 0), ia1 = scp_frag_rowmajor(lane, 1);
-    const int ib0 = scp_frag_colmajor(lane, 0), ib1 = scp_frag_colmajor(lane, 1);
-    int j = 0;
-    for (; j + 1 < nprod; j += 2) {
-        const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
-        const double a0 = A[ia0], a1 = A[ia1], b0 = B[ib0], b1 = B[ib1];
-        const double e0 = A[astride + ia0], e1 = A[astride + ia1], f0 = B[bstride + ib0], f1 = B[bstride + ib1];
-        scp_dmma(n0, n1, a0, b0);
-        scp_dmma(m0, m1, e0, f0);
-        scp_dmma(n0, n1, a1, b1);
-        scp_dmma(m0, m1, e1, f1);
-    }
-    if (j < nprod) {
-        const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
-        const double a0 = A[ia0], a1 = A[ia1], b0 = B[ib0], b1 = B[ib1];
-        scp_dmma(n0, n1, a0, b0);
-        scp_dmma(n0, n1, a1, b1);
-    }
-    n0 += m0; n1 += m1;
-    double2 c;
-    c.x = sign * n0; c.y = sign * n1;
-    *reinterpret_cast<double2 *>(out + scp_frag_c(lane)) = c;
-#else
-    if (lane == 0) {
-        double acc[64];
-        for (int e = 0; e < 64; ++e) acc[e] = 0.0;
-        for (int j = 0; j < nprod; ++j) {
-            const double *A = Abase + (size_t)j * astride, *B = Bbase + (size_t)j * bstride;
-            for (int r = 0; r < 8; ++r)
-                for (int c = 0; c < 8; ++c)
-                    for (int k = 0; k < 8; ++k) acc[r * 8 + c] += A[scp_tphys(r, k)] * B[scp_tphys(k, c)];
-        }
-        for (int r = 0; r < 8; ++r)
-            for (int c = 0; c < 8; ++c) out[scp_tphys(r, c)] = sign * acc[r * 8 + c];
-    }
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------ Cholesky
-// In-place blocked right-looking Cholesky of the tile-packed lower triangle, followed by the in-place
-// inversion of the factor: on exit m.S holds X = L^-1 (lower triangular, tile-packed).
-//
-// Why the inverse: forward/backward substitution is a dependent chain over the n1 unknowns (two synchronised
-// steps per tile column, ~13k cycles per solve at n1 = 81 on B200) and the interior-point iteration needs two
-// solves per factorisation, one after the other.  With X every solve is two triangular mat-vecs
-// (S^-1 b = X'(X b)); the inversion costs n1^3/6 multiply-adds once per factorisation on the tensor path.
-//   per tile column K:  (a) lane 0 factors the diagonal tile, (b) panel rows are solved against it by
-//   substitution (one thread per row), (c) trailing tiles -= panel panel' (one warp per tile, DMMA).
-//   then:               (d) all diagonal tiles are inverted in one phase (one thread per tile column),
-//                       (e) for K = T-2 .. 0:  W = L[K+1:,K] X_KK ;  X[K+1:,K] = -X[K+1:,K+1:] W   (DMMA).
+// In-place blocked right-looking Cholesky of the tile-packed lower triangle: on exit m.S holds L, m.dinv the
+// reciprocal pivots.
+//   per tile column K:  (a) lane 0 factors the diagonal tile (in the shadow of the previous trailing update),
+//                       (b) panel rows are solved against it by substitution (one thread per row, right-looking
+//                           inside the row: 18 cycles per unknown on the dependent chain),
+//                       (c) trailing tiles -= panel panel' (one warp per pair of tiles, DMMA).
+// The factor is NOT inverted (the previous version spent n1^3/6 multiply-adds and 2 T barriers per factorisation on
+// X = L^-1; see chol_invert_diag / chol_solve for what replaced it), and the forward substitution of ONE right-hand side
+// is free — stored as the last row of the matrix (row n1p - 1, a padding row: callers put rhs' there and a huge
+// diagonal), it is solved by the panel phases like any other row and comes out as y' = (L^-1 rhs)'.
 // *fixed is set if any pivot had to be repaired.
-SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
+SCP_FN void chol_factor(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
 {
     const int T = m.T;
-    double *S = m.S, *dinv = m.dinv, *wbuf = m.wbuf;
-    // Look-ahead: the factorisation of diagonal tile K+1 (a single-lane dependency chain, ~1.7 k cycles) runs in
-    // warp 0 during the trailing update of step K, right after that warp has updated the tile; the other warps
-    // carry the remaining tiles of the update.
+    double *S = m.S, *dinv = m.dinv;
     CTA_PHASE(tid)
         if (tid == 0) tile_potrf(S + scp_tile_off(0, 0), dinv, fixed);
     CTA_PHASE_END
@@ -294,7 +248,7 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
     for (int K = 0; K < T - 1; ++K) {
         const double *Lkk = S + scp_tile_off(K, K);
         const int Tr = T - K - 1;
-        // (b) panel rows: x L_KK' = s  ->  x[c] = (s[c] - sum_{c2<c} x[c2] L[c][c2]) dinv[c]
+        // (b) panel rows: x L_KK' = s
         CTA_PHASE(tid)
             for (int pr = tid; pr < Tr * 8; pr += cta.nt) {
                 const int I = K + 1 + (pr >> 3), r = pr & 7;
@@ -305,11 +259,9 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
                 for (int c = 0; c < 4; ++c) { x[c] = row[h0 + c]; x[c + 4] = row[h1 + c]; }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double acc = x[c];
+                    x[c] *= dinv[K * 8 + c];
 #pragma unroll
-                    for (int c2 = 0; c2 < 8; ++c2)
-                        if (c2 < c) acc -= x[c2] * Lkk[scp_tphys(c, c2)];
-                    x[c] = acc * dinv[K * 8 + c];
+                    for (int c2 = c + 1; c2 < 8; ++c2) x[c2] -= x[c] * Lkk[scp_tphys(c2, c)];
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { row[h0 + c] = x[c]; row[h1 + c] = x[c + 4]; }
@@ -348,92 +300,171 @@ SCP_FN void chol_tiles(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
         CTA_SYNC
         SCP_TIMER(4)
     }
-    // (d) invert every diagonal tile: thread (K, j) computes column j of inv(L_KK) in registers ...
-    CTA_PHASE(tid)
-        for (int t0 = 0; t0 < T * 8; t0 += cta.nt) {
-            const int t = t0 + tid;
-            if (t < T * 8) {
-                const int K = t >> 3, j = t & 7;
-                double xcol[8];
-                tile_trtri_column(S + scp_tile_off(K, K), dinv + K * 8, j, xcol);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) wbuf[K * 64 + (i << 3) + ((((j >> 2) ^ (i >> 1)) & 1) << 2) + (j & 3)] = xcol[i];
-            }
-        }
-    CTA_PHASE_END
-    // ... and the tiles are replaced once every column has been read
-    CTA_PHASE(tid)
-        for (int e = tid; e < T * 64; e += cta.nt) S[scp_tile_off(e >> 6, e >> 6) + (e & 63)] = wbuf[e];
-    CTA_PHASE_END
-    SCP_TIMER(5)
-    // (e) off-diagonal tiles of the inverse, column by column from the right
-    for (int K = T - 2; K >= 0; --K) {
-        const int Tr = T - K - 1;
-        // W_I = L_IK X_KK   (I > K), one warp per panel tile
-        WARP_SECTION(w, nw)
-            WARP_PHASE(lane)
-                for (int ii = w; ii < Tr; ii += nw)
-                    warp_tile_gemm_sum(lane, wbuf + ii * 64, S + scp_tile_off(K + 1 + ii, K), 0, S + scp_tile_off(K, K), 0, 1, 1.0);
-            WARP_PHASE_END
-        WARP_SECTION_END
-        CTA_SYNC
-        SCP_TIMER(6)
-        // X_IK = -sum_{J=K+1..I} X_IJ W_J: row ii (0-based below K) is a chain of ii + 1 tile products.  Rows are dealt
-        // to the warps longest first in snake order (w = 0..nw-1, nw-1..0, ...), which keeps the longest warp within
-        // one row of the mean for 4 and for 8 warps.
-        WARP_SECTION(w, nw)
-            WARP_PHASE(lane)
-                for (int pass = 0; pass * nw < Tr; ++pass) {
-                    const int q = pass * nw + ((pass & 1) ? nw - 1 - w : w);      // q-th longest row
-                    if (q < Tr) {
-                        const int ii = Tr - 1 - q, I = K + 1 + ii;
-                        warp_tile_gemm_sum(lane, S + scp_tile_off(I, K), S + scp_tile_off(I, K + 1), SCP_TILE2, wbuf, SCP_TILE2,
-                                           ii + 1, -1.0);
-                    }
-                }
-            WARP_PHASE_END
-        WARP_SECTION_END
-        CTA_SYNC
-        SCP_TIMER(7)
-    }
 }
 
-// v := S^-1 v = X'(X v) with X = L^-1 left in m.S by chol_tiles (v has length n1p; `tmp` is n1p scratch).
-// One thread per row (then per column) of X, four accumulators each.
-SCP_FN void chol_solve_tiles(Cta &cta, const IpmMem &m, double *v, double *tmp)
+// ---- solves: inverted diagonal tiles + tile-wise substitution by one warp -------------------------------------------
+// Substitution against L is a dependent chain over the n1 unknowns.  What was measured on B200 (n1p = 88, 3 CTAs per SM):
+//   * full inverse X = L^-1 (round 1): two mat-vecs per solve (1.8 k cycles each) but n1^3/6 multiply-adds and 2 T CTA
+//     barriers per factorisation (16 k cycles), and the explicit inverse limits the attainable dual residual;
+//   * plain tile-wise substitution by one warp, diagonal tile solved by one lane: 14 k cycles per triangular solve;
+//   * 32 x 32 diagonal blocks inverted, block substitution with lane = row: 15 k (the per-lane row-dots serialise on
+//     shared-memory latency: the compiler keeps one load in flight).
+// This version: only the 8 x 8 DIAGONAL TILES are inverted (in place, after the factorisation: one phase), and a
+// triangular solve is T steps inside warp 0 with no CTA barrier: 8 lanes apply the tile inverse (an 8 x 8 mat-vec), every
+// lane then takes the 8 new unknowns out of its rows below (forward) / columns to the left (backward).  All loads of a
+// step are issued before its arithmetic.
+#if SCP_DEVICE_BUILD
+#define SCP_LDS_FENCE asm volatile("" ::: "memory");      /* keeps the loads above, the arithmetic below */
+#endif
+
+// Replace every diagonal tile L_KK of the factor by its inverse (lower triangular, zeros above the diagonal); tiles
+// tile_base .. tile_base + 3 by this warp, lane = (tile, column).  yrow (n1p entries, or null): the warp that owns the last
+// tile first copies out row n1p - 1 (the forward-substituted right-hand side, see chol_factor), whose last entries live in
+// that tile.
+SCP_FN void warp_invert_diag_tiles(int lane, double *S, const double *dinv, int T, int tile_base, double *yrow)
+{
+#if SCP_DEVICE_BUILD
+    const int Kreal = tile_base + (lane >> 3), K = Kreal < T ? Kreal : T - 1, j = lane & 7;
+    double *Tk = S + scp_tile_off(K, K);
+    if (yrow && tile_base <= T - 1 && T - 1 < tile_base + 4) {
+        const int n1p = T * 8;
+        for (int c = lane; c < n1p; c += 32) yrow[c] = c < n1p - 1 ? S[scp_sidx(n1p - 1, c)] : 0.0;
+    }
+    double xcol[8];
+    tile_trtri_column(Tk, dinv + K * 8, j, xcol);
+    __syncwarp();
+    if (Kreal < T) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Tk[scp_tphys(i, j)] = xcol[i];
+    }
+#else
+    if (lane == 0) {
+        if (yrow && tile_base <= T - 1 && T - 1 < tile_base + 4) {
+            const int n1p = T * 8;
+            for (int c = 0; c < n1p; ++c) yrow[c] = c < n1p - 1 ? S[scp_sidx(n1p - 1, c)] : 0.0;
+        }
+        for (int K = tile_base; K < tile_base + 4 && K < T; ++K) {
+            double *Tk = S + scp_tile_off(K, K), X[64];
+            for (int j = 0; j < 8; ++j) {
+                double xcol[8];
+                tile_trtri_column(Tk, dinv + K * 8, j, xcol);
+                for (int i = 0; i < 8; ++i) X[i * 8 + j] = xcol[i];
+            }
+            for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < 8; ++j) Tk[scp_tphys(i, j)] = X[i * 8 + j];
+        }
+    }
+#endif
+}
+
+SCP_FN void chol_invert_diag(Cta &cta, const IpmMem &m, double *yrow)
+{
+    WARP_SECTION(w, nw)
+        for (int base = 4 * w; base < m.T; base += 4 * nw) {
+            WARP_PHASE(lane)
+                warp_invert_diag_tiles(lane, m.S, m.dinv, m.T, base, yrow);
+            WARP_PHASE_END
+        }
+    WARP_SECTION_END
+    CTA_SYNC
+}
+
+// data a lane keeps in a register across the warp phases of one section (the host build runs the lanes of a phase one
+// after the other, so there every lane needs its own copy)
+#if SCP_DEVICE_BUILD
+#define SCP_LANE_VAR(name) double name##_store = 0.0;
+#define SCP_LANE_REF(name, lane) name##_store
+#else
+#define SCP_LANE_VAR(name) double name##_store[32] = {0.0};
+#define SCP_LANE_REF(name, lane) name##_store[lane]
+#endif
+
+// row i of the factor against the 8 unknowns of tile column K:  sum_c L[i][8K + c] x[c]
+SCP_FN double trsv_row_dot(const double *S, int i, int K, const double *x)
+{
+    const int r = i & 7, h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;
+    const double *row = S + scp_tile_off(i >> 3, K) + (r << 3);
+#if SCP_DEVICE_BUILD
+    const double2 *row2 = reinterpret_cast<const double2 *>(row), *x2 = reinterpret_cast<const double2 *>(x);
+    const double2 r0 = row2[h0 >> 1], r1 = row2[(h0 >> 1) + 1], r2 = row2[h1 >> 1], r3 = row2[(h1 >> 1) + 1];
+    const double2 x0 = x2[0], x1 = x2[1], x2v = x2[2], x3 = x2[3];
+    SCP_LDS_FENCE
+    return ((r0.x * x0.x + r0.y * x0.y) + (r1.x * x1.x + r1.y * x1.y)) + ((r2.x * x2v.x + r2.y * x2v.y) + (r3.x * x3.x + r3.y * x3.y));
+#else
+    return ((row[h0] * x[0] + row[h0 + 1] * x[1]) + (row[h0 + 2] * x[2] + row[h0 + 3] * x[3])) +
+           ((row[h1] * x[4] + row[h1 + 1] * x[5]) + (row[h1 + 2] * x[6] + row[h1 + 3] * x[7]));
+#endif
+}
+// column j of tile row K of the factor against the 8 unknowns of that tile row:  sum_r L[8K + r][j] x[r]
+SCP_FN double trsv_col_dot(const double *S, int K, int j, const double *x)
+{
+    const int c = j & 7, lo = c & 3, he = (c >> 2) << 2, ho = he ^ 4;       // rows 0,1,4,5 / rows 2,3,6,7
+    const double *tl = S + scp_tile_off(K, j >> 3);
+    const double c0 = tl[he + lo], c1 = tl[8 + he + lo], c2 = tl[16 + ho + lo], c3 = tl[24 + ho + lo];
+    const double c4 = tl[32 + he + lo], c5 = tl[40 + he + lo], c6 = tl[48 + ho + lo], c7 = tl[56 + ho + lo];
+#if SCP_DEVICE_BUILD
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    const double2 x0 = x2[0], x1 = x2[1], x2v = x2[2], x3 = x2[3];
+    SCP_LDS_FENCE
+    return ((c0 * x0.x + c1 * x0.y) + (c2 * x1.x + c3 * x1.y)) + ((c4 * x2v.x + c5 * x2v.y) + (c6 * x3.x + c7 * x3.y));
+#else
+    return ((c0 * x[0] + c1 * x[1]) + (c2 * x[2] + c3 * x[3])) + ((c4 * x[4] + c5 * x[5]) + (c6 * x[6] + c7 * x[7]));
+#endif
+}
+
+// v := S^-1 v = L^-T (L^-1 v)   (have_y = false), or
+// v := L^-T y with y (already in v) the forward-substituted right-hand side chol_invert_diag extracted   (have_y = true),
+// for the factor prepared by chol_factor + chol_invert_diag.  v: n1p entries (zero padding).
+//
+// Tile-wise substitution across the CTA, ONE barrier per tile column, the dependent chain kept inside 8 lanes of warp 0:
+// in step K those lanes bring the rows of tile K up to date with the unknowns of tile K-1 (found in the previous step),
+// exchange them, and apply the inverse of the diagonal tile (an 8 x 8 mat-vec) to get the unknowns of tile K; meanwhile
+// every other thread takes the unknowns of tile K-1 out of one row further down.  Backward likewise with columns.
+SCP_FN void chol_solve(Cta &cta, const IpmMem &m, double *v, bool have_y)
 {
     const int T = m.T, n1p = m.n1p;
     const double *S = m.S;
-    CTA_PHASE(tid)                                  // tmp = X v
-        for (int i = tid; i < n1p; i += cta.nt) {
-            const int I = i >> 3, r = i & 7, h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int J = 0; J <= I; ++J) {
-                const double *row = S + scp_tile_off(I, J) + (r << 3);
-                const double *vj = v + J * 8;
-                a0 += row[h0] * vj[0] + row[h0 + 1] * vj[1];
-                a1 += row[h0 + 2] * vj[2] + row[h0 + 3] * vj[3];
-                a2 += row[h1] * vj[4] + row[h1 + 1] * vj[5];
-                a3 += row[h1 + 2] * vj[6] + row[h1 + 3] * vj[7];
-            }
-            tmp[i] = (a0 + a1) + (a2 + a3);
+    const int nwork = cta.nt - 8;                        // threads that work on the rows / columns beyond the current tile
+    for (int dir = have_y ? 1 : 0; dir < 2; ++dir) {
+        if (dir == 1) {
+            CTA_PHASE(tid)
+                if (tid == 0) v[n1p - 1] = 0.0;              // the right-hand-side row is not part of the system
+            CTA_PHASE_END
         }
-    CTA_PHASE_END
-    CTA_PHASE(tid)                                  // v = X' tmp
-        for (int j = tid; j < n1p; j += cta.nt) {
-            const int J = j >> 3, c = j & 7, lo = c & 3, he = (c >> 2) << 2, ho = he ^ 4;   // rows 0,1,4,5 / rows 2,3,6,7
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int I = J; I < T; ++I) {
-                const double *tl = S + scp_tile_off(I, J);
-                const double *ti = tmp + I * 8;
-                a0 += tl[he + lo] * ti[0] + tl[8 + he + lo] * ti[1];
-                a1 += tl[16 + ho + lo] * ti[2] + tl[24 + ho + lo] * ti[3];
-                a2 += tl[32 + he + lo] * ti[4] + tl[40 + he + lo] * ti[5];
-                a3 += tl[48 + ho + lo] * ti[6] + tl[56 + ho + lo] * ti[7];
-            }
-            v[j] = (a0 + a1) + (a2 + a3);
+        for (int step = 0; step < T; ++step) {
+            const int K = dir == 0 ? step : T - 1 - step;    // tile whose unknowns this step finds
+            const int Kp = dir == 0 ? K - 1 : K + 1;         // tile found in the previous step
+            WARP_SECTION(w, nw)
+                (void)nw;
+                SCP_LANE_VAR(xk)
+                WARP_PHASE(lane)
+                    const int tid = w * 32 + lane;
+                    if (step > 0) {
+                        const double *xp = v + Kp * 8;
+                        if (tid < 8) {
+                            v[K * 8 + tid] -= dir == 0 ? trsv_row_dot(S, K * 8 + tid, Kp, xp) : trsv_col_dot(S, Kp, K * 8 + tid, xp);
+                        } else {
+                            if (dir == 0) {
+                                for (int i = (K + 1) * 8 + (tid - 8); i < n1p; i += nwork) v[i] -= trsv_row_dot(S, i, Kp, xp);
+                            } else {
+                                for (int j = tid - 8; j < K * 8; j += nwork) v[j] -= trsv_col_dot(S, Kp, j, xp);
+                            }
+                        }
+                    }
+                WARP_PHASE_END
+                WARP_PHASE(lane)
+                    const int tid = w * 32 + lane;
+                    if (tid < 8)       // the diagonal tile holds its inverse
+                        SCP_LANE_REF(xk, lane) = dir == 0 ? trsv_row_dot(S, K * 8 + tid, K, v + K * 8) : trsv_col_dot(S, K, K * 8 + tid, v + K * 8);
+                WARP_PHASE_END
+                WARP_PHASE(lane)
+                    const int tid = w * 32 + lane;
+                    if (tid < 8) v[K * 8 + tid] = SCP_LANE_REF(xk, lane);
+                WARP_PHASE_END
+            WARP_SECTION_END
+            CTA_SYNC
         }
-    CTA_PHASE_END
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -458,8 +489,52 @@ SCP_FN void ipm_clear_S(Cta &cta, const IpmMem &m)
 // the regularised Newton system gives  w1 = dd rz + bs e,  dz = w1 + dd (G dx),  ds = (bs - s dz)/z.
 SCP_FN double ipm_w1(double s, double z, double rz, double e, double bs) { return z * e * rz + bs * e; }
 
+// Right-hand side of one direction computation (pass 0: affine direction, sigma mu = 0; pass 1: centring + corrector):
+//   w1 (per row, kept in dz) and  m.dx = -rx - G'w1,  padding zero.  Two phases and the operator's preparation.
+template <class Op>
+SCP_FN void ipm_pass_rhs(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, int pass, double smu)
+{
+    const int n1 = m.n1, n1p = m.n1p, mc = m.mc;
+    // w1 for the collision rows (input of A'w1); bs = -s z + sigma mu - [pass 1] (ds_a dz_a)
+    CTA_PHASE(tid)
+        for (int r = tid; r < mc; r += cta.nt) {
+            const double s = m.sA[r], z = m.zA[r];
+            double bs = smu - s * z;
+            if (pass == 1) bs -= m.ccA[r];
+            m.dzA[r] = ipm_w1(s, z, m.rzA[r], m.eA[r], bs);                       // w1 in dzA
+        }
+    CTA_PHASE_END
+    op.prep(cta, (const double *)0, m.dzA);
+    // rhs = -rx - G'w1
+    CTA_PHASE(tid)
+        for (int c = tid; c < n1p; c += cta.nt) {
+            double rhs = 0.0;
+            if (c < n1) rhs = -m.rx[c] - op.col_dot(c);
+            if (ipm_has_ub(m, ctl, c)) {
+                const double s = m.sU[c], z = m.zU[c];
+                double bs = smu - s * z;
+                if (pass == 1) bs -= m.ccU[c];
+                const double w1 = ipm_w1(s, z, s + m.x[c] - m.ub[c], m.eU[c], bs);
+                m.dzU[c] = w1; rhs -= w1;
+            }
+            if (ipm_has_lb(m, ctl, c)) {
+                const double s = m.sL[c], z = m.zL[c];
+                double bs = smu - s * z;
+                if (pass == 1) bs -= m.ccL[c];
+                const double w1 = ipm_w1(s, z, s - m.x[c] + m.lb[c], m.eL[c], bs);
+                m.dzL[c] = w1; rhs += w1;
+            }
+            m.dx[c] = rhs;
+        }
+    CTA_PHASE_END
+}
+
 // On entry m.q, m.bA, m.ub, m.lb hold the problem data (padding of q/ub/lb beyond n1 is ignored).
 // On exit m.x holds the solution.
+//
+// One iteration = residuals -> right-hand side of the affine direction -> normal matrix (that right-hand side rides as
+// its last row) -> factorisation -> [back substitution, step length] -> right-hand side of the corrector -> [forward +
+// back substitution, step length] -> update.
 template <class Op>
 SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmResult *res)
 {
@@ -493,21 +568,23 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
     } else {
         // ---- starting point (coneqp): (P + G'G) x = G'h - q ; z = Gx - h ; s = -z ; shift ------------
         SCP_TIMER(0)
-        op.form_normal(cta, m, m.dsA, m.tn, [](int) { return 1.0; },                         // dd = 1
-                       [&](int c) { return (ipm_has_ub(m, ctl, c) ? 1.0 : 0.0) + (ipm_has_lb(m, ctl, c) ? 1.0 : 0.0); }
-                       SCP_TIMER_PASS);
         op.prep(cta, (const double *)0, m.bA);
         CTA_PHASE(tid)
-            for (int c = tid; c < n1; c += cta.nt) {
-                double rhs = op.col_dot(c) - m.q[c];
+            for (int c = tid; c < n1p; c += cta.nt) {
+                double rhs = 0.0;
+                if (c < n1) rhs = op.col_dot(c) - m.q[c];
                 if (ipm_has_ub(m, ctl, c)) rhs += m.ub[c];
                 if (ipm_has_lb(m, ctl, c)) rhs += m.lb[c];
                 m.x[c] = rhs;
             }
         CTA_PHASE_END
+        op.form_normal(cta, m, m.dsA, m.tn, m.x, [](int) { return 1.0; },                    // dd = 1
+                       [&](int c) { return (ipm_has_ub(m, ctl, c) ? 1.0 : 0.0) + (ipm_has_lb(m, ctl, c) ? 1.0 : 0.0); }
+                       SCP_TIMER_PASS);
         SCP_TIMER(1)
-        chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
-        chol_solve_tiles(cta, m, m.x, m.tn);
+        chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
+        chol_invert_diag(cta, m, m.x);
+        chol_solve(cta, m, m.x, true);
         SCP_TIMER(8)
         op.prep(cta, m.x, (const double *)0);
         CTA_RED_BEGIN(cta, 3)
@@ -619,8 +696,10 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         }
         SCP_TIMER(9)
 
-        // ---- normal matrix with dd = z e and its inverted factor -----------------------------------
-        op.form_normal(cta, m, m.dsA, m.tn, [&](int r) { return m.zA[r] * m.eA[r]; },            // dd (kept in dsA)
+        // ---- affine right-hand side, then the normal matrix with dd = z e (the right-hand side as its last row) ----
+        ipm_pass_rhs(cta, op, m, ctl, 0, 0.0);
+        SCP_TIMER(10)
+        op.form_normal(cta, m, m.dsA, m.tn, m.dx, [&](int r) { return m.zA[r] * m.eA[r]; },       // dd (kept in dsA)
                        [&](int c) {
                            double d = 0.0;
                            if (ipm_has_ub(m, ctl, c)) d += m.zU[c] * m.eU[c];
@@ -628,46 +707,19 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                            return d;
                        } SCP_TIMER_PASS);
         SCP_TIMER(1)
-        chol_tiles(cta, m, fixed_p SCP_TIMER_PASS);
+        chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
+        chol_invert_diag(cta, m, m.dx);
+        SCP_TIMER(5)
 
         const double mu = gap / mrows;
         double sigma = 0.0, step = 1.0;
         for (int pass = 0; pass < 2; ++pass) {
             const double smu = sigma * mu;
-            // w1 for the collision rows (input of A'w1); bs = -s z + sigma mu - [pass 1] (ds_a dz_a)
-            CTA_PHASE(tid)
-                for (int r = tid; r < mc; r += cta.nt) {
-                    const double s = m.sA[r], z = m.zA[r];
-                    double bs = smu - s * z;
-                    if (pass == 1) bs -= m.ccA[r];
-                    m.dzA[r] = ipm_w1(s, z, m.rzA[r], m.eA[r], bs);                       // w1 in dzA
-                }
-            CTA_PHASE_END
-            op.prep(cta, (const double *)0, m.dzA);
-            // rhs = -rx - G'w1
-            CTA_PHASE(tid)
-                for (int c = tid; c < n1p; c += cta.nt) {
-                    double rhs = 0.0;
-                    if (c < n1) rhs = -m.rx[c] - op.col_dot(c);
-                    if (ipm_has_ub(m, ctl, c)) {
-                        const double s = m.sU[c], z = m.zU[c];
-                        double bs = smu - s * z;
-                        if (pass == 1) bs -= m.ccU[c];
-                        const double w1 = ipm_w1(s, z, s + m.x[c] - m.ub[c], m.eU[c], bs);
-                        m.dzU[c] = w1; rhs -= w1;
-                    }
-                    if (ipm_has_lb(m, ctl, c)) {
-                        const double s = m.sL[c], z = m.zL[c];
-                        double bs = smu - s * z;
-                        if (pass == 1) bs -= m.ccL[c];
-                        const double w1 = ipm_w1(s, z, s - m.x[c] + m.lb[c], m.eL[c], bs);
-                        m.dzL[c] = w1; rhs += w1;
-                    }
-                    m.dx[c] = rhs;
-                }
-            CTA_PHASE_END
-            SCP_TIMER(10)
-            chol_solve_tiles(cta, m, m.dx, m.tn);
+            if (pass == 1) {
+                ipm_pass_rhs(cta, op, m, ctl, 1, smu);
+                SCP_TIMER(10)
+            }
+            chol_solve(cta, m, m.dx, pass == 0);
             SCP_TIMER(8)
             op.prep(cta, m.dx, (const double *)0);
             CTA_RED_BEGIN(cta, 3)

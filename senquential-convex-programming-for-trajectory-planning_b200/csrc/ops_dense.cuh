@@ -40,7 +40,7 @@ struct DenseOp {
 
     // S(lower) = P + A' diag(dd) A + diag(dg): clear, then accumulate
     template <class Mem, class DD, class DG>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, DD ddf, DG dgf SCP_TIMER_ARG)
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, const double *rhs_row, DD ddf, DG dgf SCP_TIMER_ARG)
     {
         CTA_PHASE(tid)
             const int tot = (m.T * (m.T + 1) >> 1) * SCP_TILE2;
@@ -49,7 +49,10 @@ struct DenseOp {
             for (int c = tid; c < m.n1p; c += cta.nt) dg[c] = dgf(c);
         CTA_PHASE_END
         CTA_PHASE(tid)
-            for (int c = tid; c < m.n1p; c += cta.nt) m.S[scp_sidx(c, c)] = c < n1 ? dg[c] : 1.0;
+            for (int c = tid; c < m.n1p; c += cta.nt) m.S[scp_sidx(c, c)] = c < n1 ? dg[c] : (c == m.n1p - 1 ? 1e300 : 1.0);
+            // the right-hand side rides as the last row (see chol_factor)
+            if (rhs_row)
+                for (int j = tid; j < n1; j += cta.nt) m.S[scp_sidx(m.n1p - 1, j)] = rhs_row[j];
         CTA_PHASE_END
         add_P(cta, m.S);
         add_AtDA(cta, dd, m.S);

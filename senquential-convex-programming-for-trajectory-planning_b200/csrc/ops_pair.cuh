@@ -196,6 +196,57 @@ struct PairOp {
 #endif
     }
 
+    // One diagonal (vehicle) block on the FP64 tensor path:
+    //     S[(v,a),(v,b)] = 2 H_v[a][b] + dg delta_ab + sum_{k >= max(a,b)} g_v[k-a]' M_v(k) g_v[k-b]        (a >= b)
+    // as C = G' (M G) with the contraction index kappa = 2k + c over (step, component): lane l supplies
+    // A[a = l>>2][kappa] = g_v[k-a][c] and B[kappa][b = l>>2] = (M_v(k) g_v[k-b])[c] (two multiply-adds from the
+    // aggregated 2x2 blocks), and owns C[a = l>>2][b = 2(l&3), 2(l&3)+1].  Causality skips the kappa-steps below the tile
+    // row: Hp = 10 needs 7 DMMAs per vehicle (the entry-by-entry loop it replaces was ~40 % of form_normal).
+    SCP_MFN void diag_block_mma(int lane, double *S, int v, const double *dg) const
+    {
+        const double *gv = g + (size_t)v * Hp * 2;
+        const double *Mv = Msm + (size_t)v * Hp * 3;
+        const double *Hv = H + (size_t)v * Hp * Hp;
+#if SCP_DEVICE_BUILD
+        const double2 *__restrict__ gv2 = reinterpret_cast<const double2 *>(gv);
+        const int q = lane >> 2, kq = lane & 3, c = kq & 1, kh = kq >> 1;
+        const int nt = (Hp + 7) >> 3, nks = (2 * Hp + 3) >> 2;
+        for (int ta = 0; ta < nt; ++ta) {
+            const int a = 8 * ta + q;
+            for (int tb = 0; tb <= ta; ++tb) {
+                const int b = 8 * tb + q;
+                double c0 = 0.0, c1 = 0.0;
+                for (int s = 4 * ta; s < nks; ++s) {
+                    const int k = 2 * s + kh;
+                    double ae = 0.0, be = 0.0;
+                    if (k < Hp) {
+                        if (a <= k) ae = gv[(k - a) * 2 + c];
+                        if (b <= k) { const double2 t = gv2[k - b]; be = Mv[k * 3 + c] * t.x + Mv[k * 3 + c + 1] * t.y; }
+                    }
+                    scp_dmma(c0, c1, ae, be);
+                }
+                const int b0 = 8 * tb + 2 * kq;
+                if (a < Hp) {
+                    if (b0 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0)] = c0 + 2.0 * Hv[a * Hp + b0] + (a == b0 ? dg[v * Hp + a] : 0.0);
+                    if (b0 + 1 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0 + 1)] = c1 + 2.0 * Hv[a * Hp + b0 + 1] + (a == b0 + 1 ? dg[v * Hp + a] : 0.0);
+                }
+            }
+        }
+#else
+        if (lane == 0)
+            for (int a = 0; a < Hp; ++a)
+                for (int b = 0; b <= a; ++b) {
+                    double acc = 0.0;
+                    for (int k = a; k < Hp; ++k) {
+                        const double gbx = gv[(k - b) * 2], gby = gv[(k - b) * 2 + 1];
+                        const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;
+                        acc += gv[(k - a) * 2] * bx + gv[(k - a) * 2 + 1] * by;
+                    }
+                    S[scp_sidx(v * Hp + a, v * Hp + b)] = acc + 2.0 * Hv[a * Hp + b] + (a == b ? dg[v * Hp + a] : 0.0);
+                }
+#endif
+    }
+
     // S(lower) = blkdiag(2H, 0) + A' diag(dd) A + diag(dg), every entry written exactly once (no clear, no
     // read-modify-write):
     //   diagonal blocks   S[(v,a),(v,b)] = 2H_v[a][b] + dg + sum_{k>=a} g_v[k-a]' M_v(k) g_v[k-b],
@@ -208,8 +259,10 @@ struct PairOp {
     // read the same inputs and write disjoint entries).
     // The scalings come as functions (ddf(r): row scaling, dgf(c): box term of the diagonal) evaluated inside phase 1 —
     // no separate pass over the rows; dd[r] and dg[c] are stored for phase 2.
+    // rhs_row (n1 entries, or null): stored as row n1p - 1 of S with a huge diagonal, so that the factorisation
+    // forward-substitutes it on the way (chol_factor).
     template <class Mem, class DD, class DG>
-    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, DD ddf, DG dgf SCP_TIMER_ARG)
+    SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, const double *rhs_row, DD ddf, DG dgf SCP_TIMER_ARG)
     {
         double *S = m.S;
         CTA_RED_BEGIN(cta, 1)
@@ -239,11 +292,14 @@ struct PairOp {
                 frc[c * 2] = fx; frc[c * 2 + 1] = fy;
                 Msm[c * 3] = mxx; Msm[c * 3 + 1] = mxy; Msm[c * 3 + 2] = myy;
             }
-            // padding rows/columns of S: zero off-diagonal, unit diagonal (the factorisation keeps them so)
-            for (int c = m.n1 + tid; c < m.n1p; c += cta.nt) {
+            // padding rows/columns of S: zero off-diagonal, unit diagonal (the factorisation keeps them so); the last
+            // one carries the right-hand side
+            for (int c = m.n1 + tid; c < m.n1p - 1; c += cta.nt) {
                 for (int j = 0; j < c; ++j) S[scp_sidx(c, j)] = 0.0;
                 S[scp_sidx(c, c)] = 1.0;
             }
+            for (int j = tid; j < m.n1p; j += cta.nt)
+                S[scp_sidx(m.n1p - 1, j)] = j < m.n1 ? (rhs_row ? rhs_row[j] : 0.0) : (j == m.n1p - 1 ? 1e300 : 0.0);
             CTA_RED_SUM(cta, red, 0, tid, sw)
         CTA_PHASE_END_RED(cta, red, 1)
         const double sd = cta_red_sum(cta, red, 0);
@@ -253,12 +309,15 @@ struct PairOp {
             const int npair = nVeh * (nVeh - 1) >> 1;
             WARP_SECTION(w, nw)
                 WARP_PHASE(lane)
-                    // pairs dealt out from the last warp down: the first warps carry one pair fewer and more of the
-                    // entry-by-entry work below
-                    for (int p = nw - 1 - w; p < npair; p += nw) {
-                        int i = 0, q = p;
-                        while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
-                        pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
+                    // pair blocks, then the vehicle blocks, dealt round-robin to the warps
+                    for (int p = w; p < npair + nVeh; p += nw) {
+                        if (p < npair) {
+                            int i = 0, q = p;
+                            while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
+                            pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
+                        } else {
+                            diag_block_mma(lane, S, p - npair, dg);
+                        }
                     }
                 WARP_PHASE_END
             WARP_SECTION_END
@@ -274,9 +333,9 @@ struct PairOp {
                 S[scp_sidx(n, c)] = -acc;
             }
             if (tid == 0) S[scp_sidx(n, n)] = sd + dg[n];
-            // diagonal blocks
+            // diagonal blocks entry by entry (long horizons only)
             const int per = Hp * (Hp + 1) >> 1;
-            for (int e = tid; e < nVeh * per; e += cta.nt) {
+            for (int e = tid; e < (alpha_slots == 0 ? nVeh * per : 0); e += cta.nt) {
                 const int v = e / per;
                 int a, b;
                 scp_tri_decode(e - v * per, &a, &b);

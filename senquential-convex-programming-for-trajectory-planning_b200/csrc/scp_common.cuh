@@ -16,12 +16,14 @@
 
 #if defined(__CUDACC__)
 #define SCP_FN __device__ __forceinline__
+#define SCP_NOINLINE_FN __device__ __noinline__      /* leaf routines with their own register allocation */
 #define SCP_MFN __device__ __forceinline__
 #define SCP_HDFN __host__ __device__ __forceinline__
 #define SCP_HDMFN __host__ __device__ __forceinline__
 #define SCP_DEVICE_BUILD 1
 #else
 #define SCP_FN static inline
+#define SCP_NOINLINE_FN static inline
 #define SCP_MFN inline
 #define SCP_HDFN static inline
 #define SCP_HDMFN inline

@@ -607,7 +607,7 @@ SCP_HDFN ScpBump scp_bump(double *sh, size_t sh_lim, double *gl, bool all_shared
 // ITS translation unit: units compiled for wider CTAs carry more warps)
 SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles = SCP_RED_DOUBLES)
 {
-    m.n1 = n1; m.n1p = scp_round_up(n1, SCP_TILE); m.T = m.n1p / SCP_TILE; m.mc = mc;
+    m.n1 = n1; m.n1p = ipm_padded(n1); m.T = m.n1p / SCP_TILE; m.mc = mc;
     m.red = bp.take((size_t)red_doubles);
     m.t8 = bp.take(16);
     m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
@@ -631,13 +631,6 @@ SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles 
 
 SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 {
-    // The tile scratch of the factor inversion is only live inside chol_tiles, where the row vectors dsA (the scaling
-    // consumed by form_normal), dzA and ccA (written by the passes that follow) are dead: it overlays them when they
-    // are large enough (they are carved back to back).
-    const size_t need = (size_t)(m.T * 64 > 4 * m.n1p ? m.T * 64 : 4 * m.n1p);
-    const size_t rows = (size_t)((m.mc + 1) & ~1);
-    if (3 * rows >= need) m.wbuf = m.dsA;
-    else m.wbuf = bp.take(need);
     m.S = bp.take((size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2);
 }
 

@@ -334,7 +334,7 @@ static size_t queue_bytes(long B)
 // bytes of the interior-point warm-start iterates (one per instance)
 static size_t snap_bytes(const scpb200_dims *d)
 {
-    const int n1p = scp_round_up(d->nVeh * d->Hp + 1, SCP_TILE);
+    const int n1p = ipm_padded(d->nVeh * d->Hp + 1);
     const int mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
     const size_t b = (size_t)(d->B < 1 ? 1 : d->B) * ipm_snap_doubles(n1p, mc) * sizeof(double);
     return (b + 255) & ~(size_t)255;
