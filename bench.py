@@ -314,6 +314,25 @@ def run_product(args):
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    # ---------------- rollout entry: the same closed loop, all timed steps in ONE launch ----------------
+    # (instances are independent across MPC steps: a CTA that finishes an instance's step re-queues it for the next one,
+    # so no step of the batch waits for its longest chain of QPs; results are bit-identical to the per-step calls)
+    reset()
+    bs.params.noise_counter = 0
+    if args.warmup > 0:
+        bs.rollout(args.warmup, uMax, duLim)
+    torch.cuda.synchronize(dev)
+    barrier()
+    bs.params.noise_counter = args.warmup
+    flush.zero_()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    ro = bs.rollout(args.steps, uMax, duLim)
+    r1.record()
+    barrier()
+    t_roll = r0.elapsed_time(r1) * 1e-3
+    roll_qps, roll_ipm = int(ro["qp_total"].sum().item()), int(ro["ipm_total"].sum().item())
+
     # ---------------- assembly kernel (K2) against the HBM roofline ----------------
     asm = None
     if rank == 0 and not args.skip_assembly:
@@ -338,13 +357,14 @@ def run_product(args):
 
     # ---------------- reduce over ranks ----------------
     t_max, qps_all, e2e_max, e2e_all = t_dev, qps_rank, t_e2e, e2e_qps
+    roll_t_max, roll_qps_all, roll_ipm_all = t_roll, roll_qps, roll_ipm
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_dev, t_e2e, t_roll], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank], dtype=torch.int64, device=dev)
+        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank, roll_qps, roll_ipm], dtype=torch.int64, device=dev)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        t_max, e2e_max = float(tt[0]), float(tt[1])
-        qps_all, e2e_all, ipm_all = int(cc[0]), int(cc[1]), int(cc[2])
+        t_max, e2e_max, roll_t_max = float(tt[0]), float(tt[1]), float(tt[2])
+        qps_all, e2e_all, ipm_all, roll_qps_all, roll_ipm_all = (int(v) for v in cc)
         # the optional all-gather of trajectories / statistics, off the timed path
         gathered = [torch.empty_like(bs.U) for _ in range(world)]
         dist.all_gather(gathered, bs.U)
@@ -375,6 +395,11 @@ def run_product(args):
                                         "DFMA 36.5; profiles/r01_microbench*.txt); MEASURED_PEAKS.json has no FP64 entry",
                          "algorithmic_flops_per_ipm_iteration": fit, "solve_share_of_step": float(solve_ms.sum() / step_ms.sum())},
             "roofline_assembly": asm,
+            "rollout": {"value": roll_qps_all / roll_t_max, "unit": UNIT, "ms_per_step": 1e3 * roll_t_max / args.steps,
+                        "steps_per_launch": args.steps, "qps_total": roll_qps_all, "ipm_iterations_total": roll_ipm_all,
+                        "roofline_frac": float(fit * roll_ipm_all / world / roll_t_max / 1e12 / fp64_peak),
+                        "note": "scpb200_mpc_rollout: the same closed-loop workload with all timed MPC steps of every instance in one "
+                                "launch (instances re-queued across steps inside the kernel); bit-identical results, no per-step tail"},
             "stats": {"qps_total": qps_all, "ipm_iterations_total": ipm_all, "qp_per_instance_step": qps_all / (world * B * args.steps),
                       "ipm_per_qp": ipm_all / max(1, qps_all),
                       "status_counts_rank0": dict(zip(["qp_maxiter", "qp_pivot", "scp_maxiter", "infeasible", "setup", "qp_dres_floor"],

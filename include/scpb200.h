@@ -70,7 +70,8 @@ typedef struct scpb200_params {
     int32_t max_scp_iter;    /* SCP_controller.py:86 (20) */
     int32_t obstacle_eval_mode; /* 0: every (v,o,k) once; 1: the reference's nesting (SCP_controller.py:249-263) */
     /* interior-point controls (the reference delegates these to its third-party solver) */
-    double qp_abstol, qp_reltol, qp_feastol; /* CVXOPT-style stopping rule; defaults 1e-10, 1e-10, 1e-9 */
+    double qp_abstol, qp_reltol, qp_feastol; /* CVXOPT-style stopping rule; defaults 1e-7, 1e-13, 1e-9: the absolute gap
+                              * certifies |u - u*| <= sqrt(2 gap / lambda_min) = 5e-6 (lambda_min = 2 R = 8000) */
     double qp_dual_reg;      /* proximal regularisation of s/z in the normal matrix (default 1e-11: no pivot breakdown up to Hp = 50, fewer iterations than 1e-12, and u within 2e-8 of the extended-precision minimiser where 1e-10 leaves 1e-6; swept 1e-12 ... 1e-9 on B200) */
     double inf_bound;        /* |bound| >= inf_bound means "no bound" (default 1e20, Gurobi's convention) */
     int32_t ipm_max_iter;    /* default 60 */
@@ -256,6 +257,40 @@ int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_params *p, co
                               const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
                               double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
                               double *max_violation, const int32_t *order, void *ws, void *stream);
+
+/*
+ * Rollout entry (north-star item 4: "the SCP ... loop kept on-device with noise injection for Monte-Carlo rollouts") —
+ * replaces the caller's loop main.py:98-191 for a whole batch: `nsteps` closed-loop MPC steps per instance in ONE launch.
+ * Scenarios / noise samples are independent across MPC steps as well, so a CTA that finishes an instance's SCP loop
+ * closes the loop for it and re-queues it for its next step; no step of the batch waits for its slowest instance.  Per
+ * instance and step the arithmetic is exactly that of
+ *     mode 0:  scpb200_mpc_setup -> scpb200_scp_solve -> scpb200_advance_linear          (the benchmark's loop closure)
+ *     mode 1:  scpb200_ode_predict (delay compensation) -> scpb200_mpc_setup -> scpb200_scp_solve -> scpb200_plant_step
+ * with noise_counter = p->noise_counter + step; results are bit-identical to those call sequences.
+ * All pointers are device pointers with the layouts of the per-step entry points; arrays marked (work) are per-instance
+ * scratch that holds the last step's values on return.
+ */
+typedef struct scpb200_rollout {
+    int32_t nsteps;          /* MPC steps per instance (>= 1) */
+    int32_t mode;            /* 0 or 1, see above */
+    const double *veh, *poly, *dsafe, *dsafe_obst, *obst;       /* scenario (read-only) */
+    double *x0, *u0;         /* [B,nVeh,6], [B,nVeh]: mode 0: state, advanced in place; mode 1: (work) delay-compensated state */
+    double *x_meas, *u_act;  /* mode 1: measured state / command being actuated, advanced in place (NULL in mode 0) */
+    double *ref, *g, *cterm, *H, *qv, *gamma0, *abe;            /* (work) set-up outputs */
+    int32_t *setup_status;   /* (work) may be NULL */
+    double *u;               /* [B,n] warm start of step 0 in, last solution out */
+    double *traj, *U, *obj, *max_violation;                      /* (work) last step's results; traj/obj/max_violation may be NULL */
+    int32_t *scp_iters, *ipm_iters, *status;                     /* (work) last step's counters */
+    double uMax, duLim;      /* clamp of the applied command (mode 0: |u| <= uMax; both modes: |u - u_prev| <= duLim) */
+    double mech_limit, lat_acc_limit, delay;                     /* mode 1: as scpb200_plant_step / the horizon of scpb200_ode_predict */
+    int32_t nsub_delay, nsub_plant;                              /* mode 1: RK4 substeps of the two integrations */
+    int32_t *qp_total, *ipm_total, *status_or;                   /* [B] QPs solved / interior-point iterations / OR of the status over the steps */
+    int32_t *scp_iters_hist, *status_hist;                       /* [B,nsteps] per-step records, may be NULL */
+    double *U_hist;          /* [B,nsteps,Hp,nVeh] controller outputs per step, may be NULL */
+    double *x_hist;          /* [B,nsteps+1,nVeh,6] state before step 0 and after every step, may be NULL */
+} scpb200_rollout;
+
+int scpb200_mpc_rollout(const scpb200_dims *d, const scpb200_params *p, const scpb200_rollout *r, void *ws, void *stream);
 
 #ifdef __cplusplus
 }

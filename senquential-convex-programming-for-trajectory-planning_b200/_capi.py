@@ -37,6 +37,17 @@ class Params(C.Structure):
     ]
 
 
+class Rollout(C.Structure):
+    """scpb200_rollout (include/scpb200.h)"""
+    _fields_ = ([("nsteps", C.c_int32), ("mode", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("veh", "poly", "dsafe", "dsafe_obst", "obst", "x0", "u0", "x_meas", "u_act", "ref", "g",
+                                           "cterm", "H", "qv", "gamma0", "abe", "setup_status", "u", "traj", "U", "obj",
+                                           "max_violation", "scp_iters", "ipm_iters", "status")] +
+                [(n, C.c_double) for n in ("uMax", "duLim", "mech_limit", "lat_acc_limit", "delay")] +
+                [("nsub_delay", C.c_int32), ("nsub_plant", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("qp_total", "ipm_total", "status_or", "scp_iters_hist", "status_hist", "U_hist", "x_hist")])
+
+
 def default_params_py() -> Params:
     """The values scpb200_default_params() writes (kept in sync by tests/test_capi.py)."""
     import math
@@ -44,7 +55,7 @@ def default_params_py() -> Params:
     p.dt, p.uLim, p.dsafeExtra, p.delta_tol = 0.4, math.pi / 180.0 * 3.0, 1.0, 1e-3
     p.omega_weight, p.omega_ub, p.constraint_tol = 1e5, 1e25, 2 * 2.1 * 1e-3
     p.max_scp_iter, p.obstacle_eval_mode = 20, 0
-    p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-10, 1e-10, 1e-9, 1e-11, 1e20
+    p.qp_abstol, p.qp_reltol, p.qp_feastol, p.qp_dual_reg, p.inf_bound = 1e-7, 1e-13, 1e-9, 1e-11, 1e20
     p.ipm_max_iter, p.trust_radius, p.noise_sigma, p.seed, p.instance0, p.noise_counter = 60, 1e308, 0.0, 0, 0, 0
     p.qp_warm_start, p.qp_warm_relgap, p.qp_warm_max_iter, p.qp_warm_min_iter, p.qp_warm_carry = 1, 1.0, 30, 5, 0
     p.qp_dres_floor_factor = 100
@@ -76,6 +87,7 @@ PROTOTYPES = {
     "scpb200_scp_solve": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 19,
     "scpb200_scp_solve_ordered": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 20,
     "scpb200_work_order": [C.c_int32, _P, _P, _P],
+    "scpb200_mpc_rollout": [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Rollout), _P, _P],
 }
 
 _lib = None

@@ -244,6 +244,46 @@ class BatchSCP:
         self.solve()
         return self.plant_step(x_meas, u_act, mech_limit, lat_acc_limit, duLim, nsub=nsub_plant)
 
+    def rollout(self, nsteps: int, uMax: float, duLim: float, x_meas: Optional[torch.Tensor] = None,
+                u_act: Optional[torch.Tensor] = None, mech_limit: float = 0.0, lat_acc_limit: float = 0.0, delay: float = 0.0,
+                nsub_delay: int = 144, nsub_plant: int = 64, history: bool = False):
+        """`nsteps` closed-loop MPC steps of every instance in ONE launch (scpb200_mpc_rollout).
+
+        x_meas is None: mode 0, the loop is closed on the controller's linear model exactly as
+        setup() -> solve() -> advance_linear(uMax, duLim) per step would (self.x0 / self.u0 advance in place).
+        x_meas / u_act given (device tensors, advanced in place): mode 1, every step is mpc_step(): delay compensation,
+        set-up, SCP solve, clamp + plant integration.  noise_counter of step s is params.noise_counter + s.
+        Returns dict(qp_total, ipm_total, status_or[, scp_iters_hist, status_hist, U_hist, x_hist]) of device tensors."""
+        mode = 0 if x_meas is None else 1
+        if mode == 1:
+            assert u_act is not None and x_meas.is_cuda and u_act.is_cuda and x_meas.is_contiguous() and u_act.is_contiguous()
+            assert x_meas.dtype == torch.float64 and u_act.dtype == torch.float64
+        i32 = dict(dtype=torch.int32, device=self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            out = dict(qp_total=torch.zeros(self.B, **i32), ipm_total=torch.zeros(self.B, **i32), status_or=torch.zeros(self.B, **i32))
+            if history:
+                out.update(scp_iters_hist=torch.zeros(self.B, nsteps, **i32), status_hist=torch.zeros(self.B, nsteps, **i32),
+                           U_hist=torch.zeros(self.B, nsteps, self.Hp, self.nVeh, **f64),
+                           x_hist=torch.zeros(self.B, nsteps + 1, self.nVeh, 6, **f64))
+            r = _capi.Rollout()
+            r.nsteps, r.mode = int(nsteps), mode
+            for name in ("veh", "poly", "dsafe", "dsafe_obst", "obst", "x0", "u0", "ref", "g", "cterm", "H", "qv", "gamma0", "abe",
+                         "setup_status", "u", "traj", "U", "obj", "max_violation", "scp_iters", "ipm_iters", "status"):
+                t = getattr(self, name)
+                setattr(r, name, None if t is None else t.data_ptr())
+            r.x_meas = None if x_meas is None else x_meas.data_ptr()
+            r.u_act = None if u_act is None else u_act.data_ptr()
+            r.uMax, r.duLim, r.mech_limit, r.lat_acc_limit, r.delay = float(uMax), float(duLim), float(mech_limit), float(lat_acc_limit), float(delay)
+            r.nsub_delay, r.nsub_plant = int(nsub_delay), int(nsub_plant)
+            for name in ("qp_total", "ipm_total", "status_or", "scp_iters_hist", "status_hist", "U_hist", "x_hist"):
+                setattr(r, name, out[name].data_ptr() if name in out else None)
+            check(self.lib.scpb200_mpc_rollout(C.byref(self.dims), C.byref(self.params), C.byref(r), _ptr(self.ws), self._stream()),
+                  "scpb200_mpc_rollout")
+        self.kernel_launches += 2          # k_queue_init + k_scp_solve
+        self._have_work = False
+        return out
+
     def ode_predict(self, x: torch.Tensor, u_ref: torch.Tensor, T: float, steps: int = 10, nsub: int = 16):
         """Delay-compensation prediction (MPC_Iter.py:25-33) for the batch; returns [B,nVeh,steps,6]."""
         x, u_ref = self._dev(x), self._dev(u_ref)

@@ -1,6 +1,6 @@
 """Build libscpb200.so in-tree with nvcc for sm_100a (the only target).
 
-The library is seven translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
+The library is ten translation units — the host API with the small kernels (scpb200.cu), the SCP kernel with run-time
 dimensions (scp_solve_generic.cu, once for CTAs of up to 256 threads and once for up to 512) and with the literal
 dimensions of the shapes BASELINE.json names (scp_solve_fixed.cu: 8 vehicles x Hp 10 at two CTA widths, 8 vehicles x
 Hp 20 at two) — compiled in parallel and linked into one shared object."""
@@ -22,9 +22,12 @@ UNITS = [("scpb200.o", "scpb200.cu", []),
          ("scp_solve_v8h10_128.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=10", "-DSCP_FIXED_NT=128"]),
          ("scp_solve_v8h20_256.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=256"]),
          ("scp_solve_v8h20_512.o", "scp_solve_fixed.cu", ["-DSCP_FIXED_HP=20", "-DSCP_FIXED_NT=512"]),
-         ("scp_solve_generic_wide.o", "scp_solve_generic.cu", ["-DSCP_GENERIC_WIDE"])]
+         ("scp_solve_generic_wide.o", "scp_solve_generic.cu", ["-DSCP_GENERIC_WIDE"]),
+         ("scp_rollout_generic.o", "scp_rollout_generic.cu", []),
+         ("scp_rollout_generic_wide.o", "scp_rollout_generic.cu", ["-DSCP_GENERIC_WIDE"]),
+         ("scp_rollout_v8h10_128.o", "scp_rollout_fixed.cu", [])]
 DEPS = ["scp_common.cuh", "ipm_core.cuh", "ops_pair.cuh", "ops_dense.cuh", "scp_kernels.cuh", "scp_solve_kernel.cuh",
-        "scpb200.cu", "scp_solve_generic.cu", "scp_solve_fixed.cu", os.path.join("..", "..", "include", "scpb200.h")]
+        "scpb200.cu", "scp_solve_generic.cu", "scp_solve_fixed.cu", "scp_rollout_generic.cu", "scp_rollout_fixed.cu", os.path.join("..", "..", "include", "scpb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 

@@ -24,6 +24,7 @@ struct PairOp {
     double *red;          // reduction scratch
     double *Msm;          // [n][3] scratch: per (vehicle, step) sum of 4 dd dbar dbar' (xx, xy, yy)
     const int *rowtab;    // [mc] (i*Hp + k) | (j*Hp + k) << 16 per row (shared; built once per instance)
+    bool coh;             // H was written during this launch (rollout entry): read it past L1
     int alpha_slots;      // pair-block mode: > 0 tensor path (pair_block_mma, Hp <= 64), 0 entry by entry
 
     SCP_MFN int pair_index(int i, int j) const { return i * nVeh - (i * (i + 1) >> 1) + (j - i - 1); }
@@ -36,8 +37,8 @@ struct PairOp {
         const double *Hr = H + (size_t)c * Hp, *xv = x + v * Hp;
         double a0 = 0.0, a1 = 0.0;
         int b = 0;
-        for (; b + 1 < Hp; b += 2) { a0 += Hr[b] * xv[b]; a1 += Hr[b + 1] * xv[b + 1]; }
-        if (b < Hp) a0 += Hr[b] * xv[b];
+        for (; b + 1 < Hp; b += 2) { a0 += scp_ldc(Hr + b, coh) * xv[b]; a1 += scp_ldc(Hr + b + 1, coh) * xv[b + 1]; }
+        if (b < Hp) a0 += scp_ldc(Hr + b, coh) * xv[b];
         return 2.0 * (a0 + a1);
     }
 
@@ -227,8 +228,8 @@ struct PairOp {
                 }
                 const int b0 = 8 * tb + 2 * kq;
                 if (a < Hp) {
-                    if (b0 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0)] = c0 + 2.0 * Hv[a * Hp + b0] + (a == b0 ? dg[v * Hp + a] : 0.0);
-                    if (b0 + 1 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0 + 1)] = c1 + 2.0 * Hv[a * Hp + b0 + 1] + (a == b0 + 1 ? dg[v * Hp + a] : 0.0);
+                    if (b0 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0)] = c0 + 2.0 * scp_ldc(Hv + a * Hp + b0, coh) + (a == b0 ? dg[v * Hp + a] : 0.0);
+                    if (b0 + 1 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0 + 1)] = c1 + 2.0 * scp_ldc(Hv + a * Hp + b0 + 1, coh) + (a == b0 + 1 ? dg[v * Hp + a] : 0.0);
                 }
             }
         }
@@ -242,7 +243,7 @@ struct PairOp {
                         const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;
                         acc += gv[(k - a) * 2] * bx + gv[(k - a) * 2 + 1] * by;
                     }
-                    S[scp_sidx(v * Hp + a, v * Hp + b)] = acc + 2.0 * Hv[a * Hp + b] + (a == b ? dg[v * Hp + a] : 0.0);
+                    S[scp_sidx(v * Hp + a, v * Hp + b)] = acc + 2.0 * scp_ldc(Hv + a * Hp + b, coh) + (a == b ? dg[v * Hp + a] : 0.0);
                 }
 #endif
     }
@@ -341,7 +342,7 @@ struct PairOp {
                 scp_tri_decode(e - v * per, &a, &b);
                 const double *gv = g + (size_t)v * Hp * 2;
                 const double *Mv = Msm + (size_t)v * Hp * 3;
-                double acc = 2.0 * H[((size_t)v * Hp + a) * Hp + b] + (a == b ? dg[v * Hp + a] : 0.0);
+                double acc = 2.0 * scp_ldc(H + ((size_t)v * Hp + a) * Hp + b, coh) + (a == b ? dg[v * Hp + a] : 0.0);
                 for (int k = a; k < Hp; ++k) {
                     const double gbx = gv[(k - b) * 2], gby = gv[(k - b) * 2 + 1];
                     const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;

@@ -16,7 +16,7 @@
 
 #if defined(__CUDACC__)
 #define SCP_FN __device__ __forceinline__
-#define SCP_NOINLINE_FN __device__ __noinline__      /* leaf routines with their own register allocation */
+#define SCP_NOINLINE_FN static __device__ __noinline__      /* leaf routines with their own register allocation */
 #define SCP_MFN __device__ __forceinline__
 #define SCP_HDFN __host__ __device__ __forceinline__
 #define SCP_HDMFN __host__ __device__ __forceinline__
@@ -179,6 +179,18 @@ static __device__ unsigned long long g_scp_prof[32];   // one copy per translati
 #else
 #define SCP_LD_COHERENT(ptr) (*(ptr))
 #endif
+
+// Data that another CTA may have written during this launch and that this SM may hold in L1 from before (the rollout
+// entry re-runs the set-up of an instance on whichever CTA pops it): `coh` selects loads that bypass L1.
+SCP_FN double scp_ldc(const double *ptr, bool coh)
+{
+#if SCP_DEVICE_BUILD
+    return coh ? __ldcg(ptr) : *ptr;
+#else
+    (void)coh;
+    return *ptr;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------ misc
 SCP_HDFN int scp_imin(int a, int b) { return a < b ? a : b; }

@@ -273,17 +273,240 @@ SCP_HDFN int scp_setup_vehicle(int Hp, int nPts, double dt, const double *x, dou
     return rc;
 }
 
+// ---- K1 on a warp (device): one warp per (instance, vehicle), 8x8 matrices row-major in shared memory, every 8x8x8
+// product as two FP64 mma.m8n8k4 (the contraction north-star item (1) names), no thread-local matrix arrays.
+// Lane l owns elements 2l, 2l+1 of a row-major 8x8 matrix — exactly its accumulator fragment, so element-wise steps
+// follow a product without an exchange.
+#define SCP_K1_WARP_DOUBLES 512      /* shared scratch per warp: 7 matrices (448) + recurrence vectors (64) */
+#if SCP_DEVICE_BUILD
+SCP_FN void warp_mm8(int lane, const double *X, const double *Y, double *C)      // C = X Y (C aliases neither)
+{
+    const int r = lane >> 2, q = lane & 3;
+    double c0 = 0.0, c1 = 0.0;
+    const double x0 = X[r * 8 + q], x1 = X[r * 8 + q + 4], y0 = Y[q * 8 + r], y1 = Y[(q + 4) * 8 + r];
+    scp_dmma(c0, c1, x0, y0);
+    scp_dmma(c0, c1, x1, y1);
+    double2 c;
+    c.x = c0; c.y = c1;
+    reinterpret_cast<double2 *>(C)[lane] = c;
+    __syncwarp();
+}
+
+// W := expm(A) (A is scaled in place), degree-13 Pade with scaling and squaring as scp_expm8; ws = 6 matrices.
+// Returns 0, or -1 if the Pade denominator is singular (warp-uniform).
+SCP_FN int warp_expm8(int lane, double *A, double *ws)
+{
+    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                          129060195264000.,   10559470521600.,    670442572800.,     33522128640.,
+                          1323241920.,        40840800.,          960960.,           16380., 182., 1.};
+    double *A2 = ws, *A4 = ws + 64, *A6 = ws + 128, *U = ws + 192, *V = ws + 256, *W = ws + 320;
+    const int e0 = 2 * lane, e1 = e0 + 1;
+    const bool d0 = (e0 >> 3) == (e0 & 7), d1 = (e1 >> 3) == (e1 & 7);
+    double cs = 0.0;
+    if (lane < 8)
+        for (int i = 0; i < 8; ++i) cs += fabs(A[i * 8 + lane]);
+    const double nrm = scp_warp_max(cs);
+    int s = 0;
+    if (nrm > 5.371920351148152) {
+        s = (int)ceil(log2(nrm / 5.371920351148152));
+        if (s < 0) s = 0;
+    }
+    const double sc = ldexp(1.0, -s);
+    __syncwarp();
+    A[e0] *= sc; A[e1] *= sc;
+    __syncwarp();
+    warp_mm8(lane, A, A, A2);
+    warp_mm8(lane, A2, A2, A4);
+    warp_mm8(lane, A4, A2, A6);
+    W[e0] = b[13] * A6[e0] + b[11] * A4[e0] + b[9] * A2[e0];
+    W[e1] = b[13] * A6[e1] + b[11] * A4[e1] + b[9] * A2[e1];
+    __syncwarp();
+    warp_mm8(lane, A6, W, V);
+    V[e0] += b[7] * A6[e0] + b[5] * A4[e0] + b[3] * A2[e0]; if (d0) V[e0] += b[1];
+    V[e1] += b[7] * A6[e1] + b[5] * A4[e1] + b[3] * A2[e1]; if (d1) V[e1] += b[1];
+    __syncwarp();
+    warp_mm8(lane, A, V, U);
+    W[e0] = b[12] * A6[e0] + b[10] * A4[e0] + b[8] * A2[e0];
+    W[e1] = b[12] * A6[e1] + b[10] * A4[e1] + b[8] * A2[e1];
+    __syncwarp();
+    warp_mm8(lane, A6, W, V);
+    V[e0] += b[6] * A6[e0] + b[4] * A4[e0] + b[2] * A2[e0]; if (d0) V[e0] += b[0];
+    V[e1] += b[6] * A6[e1] + b[4] * A4[e1] + b[2] * A2[e1]; if (d1) V[e1] += b[0];
+    __syncwarp();
+    // solve (V - U) X = (V + U): Gaussian elimination with partial pivoting on [Q | R], Q in A2, R in W; lane c < 16 owns
+    // column c of the 8 x 16 array, the pivot search is done by every lane alike
+    {
+        const double q0 = V[e0] - U[e0], q1 = V[e1] - U[e1], r0 = V[e0] + U[e0], r1 = V[e1] + U[e1];
+        A2[e0] = q0; A2[e1] = q1; W[e0] = r0; W[e1] = r1;
+    }
+    __syncwarp();
+    double *col = lane < 8 ? A2 + lane : W + (lane - 8);
+    int fail = 0;
+    for (int k = 0; k < 8; ++k) {
+        int piv = k;
+        double best = fabs(A2[k * 8 + k]);
+        for (int i = k + 1; i < 8; ++i) {
+            const double t = fabs(A2[i * 8 + k]);
+            if (t > best) { best = t; piv = i; }
+        }
+        if (best == 0.0) { fail = 1; break; }
+        double li[8];
+        const double pk = A2[piv * 8 + k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int src = i == k ? piv : (i == piv ? k : i);          // row i after the swap
+            li[i] = A2[src * 8 + k] / pk;
+        }
+        __syncwarp();
+        if (lane < 16 && (lane > k || lane >= 8)) {
+            if (piv != k) { const double t = col[k * 8]; col[k * 8] = col[piv * 8]; col[piv * 8] = t; }
+            const double ck = col[k * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i > k) col[i * 8] -= li[i] * ck;
+        } else if (lane <= k && piv != k) {
+            const double t = col[k * 8]; col[k * 8] = col[piv * 8]; col[piv * 8] = t;      // columns already eliminated: swap only
+        }
+        __syncwarp();
+    }
+    if (fail) return -1;
+    if (lane < 8) {
+        double *rc = W + lane;
+        for (int i = 7; i >= 0; --i) {
+            double acc = rc[i * 8];
+            for (int k = i + 1; k < 8; ++k) acc -= A2[i * 8 + k] * rc[k * 8];
+            rc[i * 8] = acc / A2[i * 8 + i];
+        }
+    }
+    __syncwarp();
+    for (int k = 0; k < s; ++k) {
+        warp_mm8(lane, W, W, V);
+        W[e0] = V[e0]; W[e1] = V[e1];
+        __syncwarp();
+    }
+    return 0;
+}
+
+// scp_setup_vehicle by one warp.  ws: SCP_K1_WARP_DOUBLES of shared scratch.  x (6), pv (5), poly read from anywhere.
+SCP_FN int warp_setup_vehicle(int lane, int Hp, int nPts, double dt, const double *x, double u0, const double *pv,
+                              const double *poly, const double *noise, double *ref, double *g, double *cterm, double *abe,
+                              double *ws)
+{
+    double *M = ws, *mats = ws + 64, *E = ws + 64 + 320, *vec = ws + 448;     // vec: CA[12] SM[12] CB[12] (double-buffered CA)
+    M[2 * lane] = 0.0; M[2 * lane + 1] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        const double Lf = pv[0], Lr = pv[1], Ls = Lf + Lr;
+        const double t5 = tan(x[5]);
+        const double w = sqrt((Lr * Lr * t5 * t5) / (Ls * Ls) + 1.0);
+        const double ang = x[2] + atan((Lr * t5) / Ls);
+        const double sa = sin(ang), ca = cos(ang), sec2 = t5 * t5 + 1.0;
+        M[0 * 8 + 2] = -x[3] * sa * w;
+        M[0 * 8 + 3] = ca * w;
+        M[0 * 8 + 5] = (Lr * Lr * x[3] * ca * t5 * sec2) / (w * Ls * Ls) - (Lr * x[3] * sa * sec2) / (w * Ls);
+        M[1 * 8 + 2] = x[3] * ca * w;
+        M[1 * 8 + 3] = sa * w;
+        M[1 * 8 + 5] = (Lr * x[3] * ca * sec2) / (w * Ls) + (Lr * Lr * x[3] * sa * t5 * sec2) / (w * Ls * Ls);
+        M[2 * 8 + 3] = t5 / Ls;
+        M[2 * 8 + 5] = (x[3] * sec2) / Ls;
+        M[3 * 8 + 4] = 1.0;
+        M[5 * 8 + 5] = -10.0;
+        M[5 * 8 + 6] = 10.0;                                    // Bc
+        double f[6];
+        scp_bicycle_rhs(x, u0, Lf, Lr, f);
+        if (noise) { f[0] += noise[0]; f[1] += noise[1]; }
+        for (int i = 0; i < 6; ++i) {                           // Ec = f - Ac x - Bc u  (Model.py:58)
+            double acc = f[i];
+            for (int j = 0; j < 6; ++j) acc -= M[i * 8 + j] * x[j];
+            M[i * 8 + 7] = acc - M[i * 8 + 6] * u0;
+        }
+    }
+    int rc = 0;
+    // the sampler does not depend on the exponential: one lane of the otherwise idle half
+    if (lane == 31 && scp_sample_reference(Hp, nPts, poly, x[0], x[1], x[3] * dt, ref)) rc = SCPB200_ST_SETUP;
+    __syncwarp();
+    M[2 * lane] *= dt; M[2 * lane + 1] *= dt;
+    __syncwarp();
+    if (warp_expm8(lane, M, mats)) rc = SCPB200_ST_SETUP;
+    // E (row-major 8x8): Ad = E[0:6,0:6], Bd = E[0:6,6], Ed = E[0:6,7] with |Ed| <= 1e-30 -> 0 (MPC_Iter.py:87)
+    if (lane < 6) {
+        const double ed = E[lane * 8 + 7];
+        if (fabs(ed) <= 1e-30) E[lane * 8 + 7] = 0.0;
+    }
+    __syncwarp();
+    if (abe) {
+        for (int i = lane; i < 36; i += 32) abe[i] = E[(i / 6) * 8 + (i % 6)];
+        if (lane < 6) { abe[36 + lane] = E[lane * 8 + 6]; abe[42 + lane] = E[lane * 8 + 7]; }
+    }
+    // recurrences (MPC_Iter.py:129-149): CA_{i+1} = CA_i Ad, g_i = CA_i Bd, c(k) = CA_{k+1} x0 + (sum_{l<=k} CA_l) Ed; lanes
+    // 0..11 own the entries of CA / its running sum, lanes 12, 13 the two components of g, lanes 14, 15 those of c
+    double *CA = vec, *SM = vec + 12, *CB = vec + 24;
+    const int r = lane < 12 ? lane / 6 : (lane & 1), j = lane < 12 ? lane - 6 * (lane / 6) : 0;
+    double ca = 0.0, sm = 0.0;
+    if (lane < 12) { ca = (lane == 0 || lane == 7) ? 1.0 : 0.0; CA[lane] = ca; }
+    __syncwarp();
+    for (int k = 0; k < Hp; ++k) {
+        double *cur = (k & 1) ? CB : CA, *nxt = (k & 1) ? CA : CB;
+        if (lane < 12) {
+            sm += ca;
+            SM[lane] = sm;
+            double acc = 0.0;
+            for (int l = 0; l < 6; ++l) acc += cur[r * 6 + l] * E[l * 8 + j];
+            ca = acc;
+            nxt[lane] = ca;
+        } else if (lane < 14) {
+            double acc = 0.0;
+            for (int jj = 0; jj < 6; ++jj) acc += cur[r * 6 + jj] * E[jj * 8 + 6];
+            g[k * 2 + r] = acc;
+        }
+        __syncwarp();
+        if (lane == 14 || lane == 15) {
+            double acc = 0.0, acc2 = 0.0;
+            for (int jj = 0; jj < 6; ++jj) { acc += nxt[r * 6 + jj] * x[jj]; acc2 += SM[r * 6 + jj] * E[jj * 8 + 7]; }
+            cterm[k * 2 + r] = acc + acc2;
+        }
+        __syncwarp();
+    }
+    return __any_sync(0xffffffffu, rc != 0) ? SCPB200_ST_SETUP : 0;
+}
+#endif
+
 // K1, one CTA per instance: phase 1 one thread per vehicle (serial expm/recurrences), phase 2 all threads on
 // the cost matrices of MPC_Iter.py:116-127:  H = B'QB + R,  qv = -2 B'Q(Ref - c),  gamma0 = sum_v Err'Q Err.
-SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const double *x0,
-                               const double *u0, const double *veh, const double *poly, double *ref, double *g,
-                               double *cterm, double *H, double *qv, double *gamma0, double *abe,
-                               int32_t *setup_status, double *red, int *flag)
+// x0b / u0b: the instance's own states ([nVeh][6], [nVeh]); every other array is a batch base indexed with b.
+// coh: the instance's arrays may have been written by another CTA during this launch (rollout entry): read them past L1.
+SCP_FN void scp_setup_instance_at(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const double *x0b,
+                                  const double *u0b, const double *veh, const double *poly, double *ref, double *g,
+                                  double *cterm, double *H, double *qv, double *gamma0, double *abe,
+                                  int32_t *setup_status, double *red, int *flag, bool coh, double *k1ws, int k1_warps = 1 << 30)
 {
     const int nVeh = d.nVeh, Hp = d.Hp, nPts = d.nPts;
     CTA_PHASE(tid)
         if (tid == 0) *flag = 0;
     CTA_PHASE_END
+#if SCP_DEVICE_BUILD
+    // one warp per vehicle (warp_setup_vehicle), scratch SCP_K1_WARP_DOUBLES per warp
+    {
+        const int w = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, nw = scp_imin(cta.nt >> 5, k1_warps);
+        for (int v = w; v < nVeh && w < nw; v += nw) {
+            const size_t iv = (size_t)b * nVeh + v;
+            double nz[2];
+            const double *noise = 0;
+            if (p.noise_sigma > 0.0) {
+                scp_noise_pair(p.seed, p.instance0 + (uint32_t)b, (uint32_t)v, p.noise_counter, nz);
+                nz[0] *= p.noise_sigma;
+                nz[1] *= p.noise_sigma;
+                noise = nz;
+            }
+            const int rc = warp_setup_vehicle(lane, Hp, nPts, p.dt, x0b + v * 6, u0b[v], veh + iv * 5, poly + iv * nPts * 2, noise,
+                                              ref + iv * Hp * 2, g + iv * Hp * 2, cterm + iv * Hp * 2, abe ? abe + iv * 48 : 0,
+                                              k1ws + (size_t)w * SCP_K1_WARP_DOUBLES);
+            if (rc && lane == 0) *flag = rc;
+        }
+    }
+    __syncthreads();
+#else
+    (void)k1ws;
     CTA_PHASE(tid)
         for (int v = tid; v < nVeh; v += cta.nt) {
             const size_t iv = (size_t)b * nVeh + v;
@@ -295,12 +518,13 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
                 nz[1] *= p.noise_sigma;
                 noise = nz;
             }
-            const int rc = scp_setup_vehicle(Hp, nPts, p.dt, x0 + iv * 6, u0[iv], veh + iv * 5, poly + iv * nPts * 2,
+            const int rc = scp_setup_vehicle(Hp, nPts, p.dt, x0b + v * 6, u0b[v], veh + iv * 5, poly + iv * nPts * 2,
                                              noise, ref + iv * Hp * 2, g + iv * Hp * 2, cterm + iv * Hp * 2,
                                              abe ? abe + iv * 48 : 0);
             if (rc) *flag = rc;
         }
     CTA_PHASE_END
+#endif
     CTA_RED_BEGIN(cta, 1)
     CTA_PHASE(tid)
         double gam = 0.0;
@@ -312,7 +536,8 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             double acc = 0.0;
             for (int i = (a > bb ? a : bb); i < Hp; ++i) {
                 const double wq = (i == Hp - 1) ? Qf : Q;
-                acc += wq * (gv[(i - a) * 2] * gv[(i - bb) * 2] + gv[(i - a) * 2 + 1] * gv[(i - bb) * 2 + 1]);
+                acc += wq * (scp_ldc(gv + (i - a) * 2, coh) * scp_ldc(gv + (i - bb) * 2, coh) +
+                             scp_ldc(gv + (i - a) * 2 + 1, coh) * scp_ldc(gv + (i - bb) * 2 + 1, coh));
             }
             H[iv * Hp * Hp + a * Hp + bb] = acc + (a == bb ? R : 0.0);
         }
@@ -324,11 +549,12 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             double acc = 0.0;
             for (int i = a; i < Hp; ++i) {
                 const double wq = (i == Hp - 1) ? Qf : Q;
-                acc += wq * (gv[(i - a) * 2] * (rv[i * 2] - cv[i * 2]) + gv[(i - a) * 2 + 1] * (rv[i * 2 + 1] - cv[i * 2 + 1]));
+                acc += wq * (scp_ldc(gv + (i - a) * 2, coh) * (scp_ldc(rv + i * 2, coh) - scp_ldc(cv + i * 2, coh)) +
+                             scp_ldc(gv + (i - a) * 2 + 1, coh) * (scp_ldc(rv + i * 2 + 1, coh) - scp_ldc(cv + i * 2 + 1, coh)));
             }
             qv[iv * Hp + a] = -2.0 * acc;
             const double wq = (a == Hp - 1) ? Qf : Q;
-            const double ex = rv[a * 2] - cv[a * 2], ey = rv[a * 2 + 1] - cv[a * 2 + 1];
+            const double ex = scp_ldc(rv + a * 2, coh) - scp_ldc(cv + a * 2, coh), ey = scp_ldc(rv + a * 2 + 1, coh) - scp_ldc(cv + a * 2 + 1, coh);
             gam += wq * (ex * ex + ey * ey);
         }
         CTA_RED_SUM(cta, red, 0, tid, gam)
@@ -340,6 +566,15 @@ SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             if (setup_status) setup_status[b] = *flag;
         }
     CTA_PHASE_END
+}
+
+SCP_FN void scp_setup_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const double *x0,
+                               const double *u0, const double *veh, const double *poly, double *ref, double *g,
+                               double *cterm, double *H, double *qv, double *gamma0, double *abe,
+                               int32_t *setup_status, double *red, int *flag, double *k1ws = 0)
+{
+    scp_setup_instance_at(cta, d, p, b, x0 + (size_t)b * d.nVeh * 6, u0 + (size_t)b * d.nVeh, veh, poly, ref, g, cterm, H, qv,
+                          gamma0, abe, setup_status, red, flag, false, k1ws);
 }
 
 // ================================================================================================ ODE prediction
@@ -436,13 +671,14 @@ SCP_HDFN void scp_advance_vehicle(const double *abe, double u_cmd, double uMax, 
 
 // ================================================================================================ shared pieces
 // pos[(v,k)] = cterm_v(k) + sum_{a<=k} g_v[k-a] u_v[a]      (forward_U, SCP_controller.py:199-213)
-SCP_FN void scp_positions(Cta &cta, int nVeh, int Hp, const double *g, const double *cterm, const double *u, double *pos)
+SCP_FN void scp_positions(Cta &cta, int nVeh, int Hp, const double *g, const double *cterm, const double *u, double *pos,
+                          bool coh = false)
 {
     CTA_PHASE(tid)
         for (int c = tid; c < nVeh * Hp; c += cta.nt) {
             const int v = c / Hp, k = c - v * Hp;
             const double *gv = g + (size_t)v * Hp * 2;
-            double px = cterm[c * 2], py = cterm[c * 2 + 1];
+            double px = scp_ldc(cterm + c * 2, coh), py = scp_ldc(cterm + c * 2 + 1, coh);
             for (int a = 0; a <= k; ++a) {
                 px += gv[(k - a) * 2] * u[v * Hp + a];
                 py += gv[(k - a) * 2 + 1] * u[v * Hp + a];
@@ -477,10 +713,11 @@ struct ScpEval {
 SCP_FN void scp_evaluate(Cta &cta, int nVeh, int Hp, int nObst, const double *g, const double *cterm, const double *H,
                          const double *qv, double gamma0, const double *u, const double *dsafe,
                          const double *dsafe_obst, const double *obst, double dsafeExtra, double tol,
-                         int obstacle_mode, double *pos, double *red, ScpEval *out, double *ci_out, double *cio_out)
+                         int obstacle_mode, double *pos, double *red, ScpEval *out, double *ci_out, double *cio_out,
+                         bool coh = false)
 {
     const int n = nVeh * Hp, mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
-    scp_positions(cta, nVeh, Hp, g, cterm, u, pos);
+    scp_positions(cta, nVeh, Hp, g, cterm, u, pos, coh);
     CTA_RED_BEGIN(cta, 3)
     CTA_PHASE(tid)
         double po = 0.0, ps = 0.0, pm = 0.0;
@@ -488,8 +725,8 @@ SCP_FN void scp_evaluate(Cta &cta, int nVeh, int Hp, int nObst, const double *g,
             const int v = c / Hp;
             const double *Hr = H + (size_t)c * Hp;
             double acc = 0.0;
-            for (int bb = 0; bb < Hp; ++bb) acc += Hr[bb] * u[v * Hp + bb];
-            po += u[c] * (acc + qv[c]);
+            for (int bb = 0; bb < Hp; ++bb) acc += scp_ldc(Hr + bb, coh) * u[v * Hp + bb];
+            po += u[c] * (acc + scp_ldc(qv + c, coh));
         }
         if (ci_out)
             for (int e = tid; e < nVeh * nVeh * Hp; e += cta.nt) {
@@ -533,10 +770,10 @@ SCP_FN void scp_evaluate(Cta &cta, int nVeh, int Hp, int nObst, const double *g,
 // dbar[r] = relative position at ubar, bA[r] = -sbar^2 - |dbar|^2 + 2 dbar.(c_i(k) - c_j(k)).
 SCP_FN void scp_linearise(Cta &cta, int nVeh, int Hp, int nObst, const double *g, const double *cterm,
                           const double *ubar, const double *dsafe, const double *dsafe_obst, const double *obst,
-                          double dsafeExtra, double *pos, double *dbar, double *bA)
+                          double dsafeExtra, double *pos, double *dbar, double *bA, bool coh = false)
 {
     const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
-    scp_positions(cta, nVeh, Hp, g, cterm, ubar, pos);
+    scp_positions(cta, nVeh, Hp, g, cterm, ubar, pos, coh);
     CTA_PHASE(tid)
         for (int r = tid; r < mc; r += cta.nt) {
             int i, j, o, k;
@@ -545,15 +782,15 @@ SCP_FN void scp_linearise(Cta &cta, int nVeh, int Hp, int nObst, const double *g
             if (o < 0) {
                 dx = pos[(i * Hp + k) * 2] - pos[(j * Hp + k) * 2];
                 dy = pos[(i * Hp + k) * 2 + 1] - pos[(j * Hp + k) * 2 + 1];
-                bx = cterm[(i * Hp + k) * 2] - cterm[(j * Hp + k) * 2];
-                by = cterm[(i * Hp + k) * 2 + 1] - cterm[(j * Hp + k) * 2 + 1];
+                bx = scp_ldc(cterm + (i * Hp + k) * 2, coh) - scp_ldc(cterm + (j * Hp + k) * 2, coh);
+                by = scp_ldc(cterm + (i * Hp + k) * 2 + 1, coh) - scp_ldc(cterm + (j * Hp + k) * 2 + 1, coh);
                 sbar = dsafe[i * nVeh + j] + dsafeExtra;
             } else {
                 const double ox = obst[(o * Hp + k) * 2], oy = obst[(o * Hp + k) * 2 + 1];
                 dx = pos[(i * Hp + k) * 2] - ox;
                 dy = pos[(i * Hp + k) * 2 + 1] - oy;
-                bx = cterm[(i * Hp + k) * 2] - ox;
-                by = cterm[(i * Hp + k) * 2 + 1] - oy;
+                bx = scp_ldc(cterm + (i * Hp + k) * 2, coh) - ox;
+                by = scp_ldc(cterm + (i * Hp + k) * 2 + 1, coh) - oy;
                 sbar = dsafe_obst[i * nObst + o] + dsafeExtra;
             }
             dbar[r * 2] = dx;
@@ -698,6 +935,7 @@ struct ScpIO {
     double *state;      // [B][SCP_STATE_W] or null (run to completion)
     int quantum;
     double *snap;       // [B][ipm_snap_doubles] interior-point warm-start iterates, or null (every QP starts cold)
+    int coherent;       // the set-up outputs (g, cterm, H, qv, gamma0) were written during this launch: read them past L1
 };
 #define SCP_STATE_W 8   /* obj0, mv0, it, ipm_total, status bits, pinned (never parked), snapshot valid, (spare) */
 
@@ -714,7 +952,8 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     const double *dsB = io.dsafe + (size_t)b * nVeh * nVeh;
     const double *dsoB = nObst ? io.dsafe_obst + (size_t)b * nVeh * nObst : 0;
     const double *obB = nObst ? io.obst + (size_t)b * nObst * Hp * 2 : 0;
-    const double gamma0 = io.gamma0[b];
+    const bool coh = io.coherent != 0;
+    const double gamma0 = scp_ldc(io.gamma0 + b, coh);
     double *uB = io.u + (size_t)b * n;
 
     IpmCtl ctl;
@@ -731,7 +970,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
     op.g = s.g; op.H = s.H_local ? s.Hs : HB; op.dbar = s.dbar; op.resp = s.resp; op.frc = s.frc; op.red = m.red;
     op.xom = 0.0; op.wsum = 0.0;
-    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots; op.rowtab = s.rowtab;
+    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots; op.rowtab = s.rowtab; op.coh = coh;
 
     double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
     const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance
@@ -739,14 +978,14 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
 
     // instance data -> shared; warm start (SCP_controller.py:42-43) with the eps tweak of :75-76
     CTA_PHASE(tid)
-        for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = gB[e];
+        for (int e = tid; e < n * 2; e += cta.nt) s.g[e] = scp_ldc(gB + e, coh);
         for (int r = tid; r < mc; r += cta.nt) {
             int i, j, o, k;
             scp_row_decode(nVeh, Hp, nObst, mcv, r, &i, &j, &o, &k);
             s.rowtab[r] = (i * Hp + k) | ((j >= 0 ? j * Hp + k : 0xffff) << 16);
         }
         if (s.H_local)
-            for (int e = tid; e < n * Hp; e += cta.nt) s.Hs[e] = HB[e];
+            for (int e = tid; e < n * Hp; e += cta.nt) s.Hs[e] = scp_ldc(HB + e, coh);
         for (int c = tid; c < m.n1p; c += cta.nt) {
             double uv = 0.0;
             if (c < n) {
@@ -754,7 +993,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
                 if (c == 0 && it_resume == 0 && fabs(uv) < 2.220446049250313e-16) uv = 2.220446049250313e-16;
             }
             s.ucur[c] = uv;
-            m.q[c] = (c < n) ? qB[c] : (c == n ? p.omega_weight : 0.0);
+            m.q[c] = (c < n) ? scp_ldc(qB + c, coh) : (c == n ? p.omega_weight : 0.0);
         }
     CTA_PHASE_END
 
@@ -763,7 +1002,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     int it = 0, ipm_total = 0, st = 0, stopped = 0;
     if (it_resume == 0) {
         scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra, p.constraint_tol,
-                     p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
+                     p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0, coh);
         obj0 = ev.obj; mv0 = ev.max_violation;
         snap_valid = snap_carried;
     } else {
@@ -785,7 +1024,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             CTA_PHASE_END
             return false;
         }
-        scp_linearise(cta, nVeh, Hp, nObst, s.g, cB, s.ucur, dsB, dsoB, obB, p.dsafeExtra, s.resp, s.dbar, m.bA);
+        scp_linearise(cta, nVeh, Hp, nObst, s.g, cB, s.ucur, dsB, dsoB, obB, p.dsafeExtra, s.resp, s.dbar, m.bA, coh);
         CTA_PHASE(tid)
             for (int c = tid; c < m.n1p; c += cta.nt) {
                 double lo = -p.uLim, hi = p.uLim;
@@ -824,7 +1063,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
             for (int c = tid; c < n; c += cta.nt) s.ucur[c] = m.x[c];
         CTA_PHASE_END
         scp_evaluate(cta, nVeh, Hp, nObst, s.g, cB, HB, qB, gamma0, s.ucur, dsB, dsoB, obB, p.dsafeExtra,
-                     p.constraint_tol, p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0);
+                     p.constraint_tol, p.obstacle_eval_mode, s.resp, m.red, &ev, 0, 0, coh);
         const double fval = res.fval + gamma0;
         const double merit0 = obj0 + p.omega_weight * mv0;
         const double delta_hat = merit0 - fval;
@@ -852,7 +1091,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     if (!stopped) st |= SCPB200_ST_SCP_MAXITER;
     if (!ev.feasible) st |= SCPB200_ST_INFEASIBLE;
     // results: u, forward_U shapes traj[Hp][2][nVeh], U[Hp][nVeh]
-    scp_positions(cta, nVeh, Hp, s.g, cB, s.ucur, s.resp);
+    scp_positions(cta, nVeh, Hp, s.g, cB, s.ucur, s.resp, coh);
     CTA_PHASE(tid)
         for (int c = tid; c < n; c += cta.nt) {
             const int v = c / Hp, k = c - v * Hp;
@@ -873,6 +1112,110 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         }
     CTA_PHASE_END
     return true;
+}
+
+// ================================================================================================ rollout
+// Closed-loop MPC steps of ONE instance inside the solve kernel (scpb200_mpc_rollout): instances of a Monte-Carlo batch
+// are independent ACROSS MPC steps too, so a CTA that finishes an instance's SCP loop closes the loop for it (clamp +
+// plant / linear advance), runs the next step's set-up (K1) and hands the instance back to the work queue — no per-step
+// kernel boundary, hence no step that ends on its longest chain of QPs while most CTAs idle (measured: 20 % of the warp
+// samples of the per-step kernel wait at the queue).  The arithmetic per step is that of scpb200_mpc_setup ->
+// scpb200_scp_solve -> scpb200_advance_linear (mode 0) or of BatchSCP.mpc_step (mode 1): results are bit-identical.
+struct ScpRollout {
+    int nsteps;                // 0: the kernel runs in per-step mode
+    int mode;                  // 0: advance on the controller's linear model; 1: delay compensation + plant integration
+    uint32_t counter0;         // noise counter of step 0 (step s draws with counter0 + s)
+    const double *veh, *poly;  // [B,nVeh,5], [B,nVeh,nPts,2]
+    double *x0, *u0;           // [B,nVeh,6], [B,nVeh]  set-up inputs (mode 0: advanced in place; mode 1: written per step)
+    double *x_meas, *u_act;    // mode 1: measured state / command being actuated, advanced in place
+    double *ref, *g, *cterm, *H, *qv, *gamma0, *abe;   // set-up outputs (per-instance slices of the batch arrays)
+    int32_t *setup_status;
+    double uMax, duLim, mech_limit, lat_acc_limit, delay;
+    int nsub_delay, nsub_plant;
+    int32_t *qp_total, *ipm_total, *status_or;      // [B] accumulated over the steps
+    int32_t *scp_iters_hist, *status_hist;          // [B,nsteps] or null
+    double *U_hist, *x_hist;                        // [B,nsteps,Hp,nVeh], [B,nsteps+1,nVeh,6] or null
+};
+
+// Set-up of instance b for its MPC step `step`.  `stage` is CTA scratch of >= 7 nVeh doubles.
+SCP_FN void scp_rollout_setup(Cta &cta, const scpb200_dims &d, const scpb200_params &p, const ScpRollout &ro, int b, int step,
+                              double *stage, double *red, int *flag, double *k1ws, int k1_warps)
+{
+    const int nVeh = d.nVeh;
+    scpb200_params ps = p;
+    ps.noise_counter = ro.counter0 + (uint32_t)step;
+    double *xs = stage, *us = stage + (size_t)nVeh * 6;
+    CTA_PHASE(tid)
+        for (int v = tid; v < nVeh; v += cta.nt) {
+            const size_t iv = (size_t)b * nVeh + v;
+            double x[6];
+            if (ro.mode == 1) {
+                // IterClass (MPC_Iter.py:25-33): the state the command will meet, delay_x + dt + delay_u ahead
+                double xm[6], out[12];
+                for (int i = 0; i < 6; ++i) xm[i] = scp_ldc(ro.x_meas + iv * 6 + i, true);
+                const double ua = scp_ldc(ro.u_act + iv, true);
+                scp_ode_predict_vehicle(xm, ua, ro.veh[iv * 5], ro.veh[iv * 5 + 1], ro.delay, 2, ro.nsub_delay, ps.noise_sigma, ps.seed,
+                                        ps.instance0 + (uint32_t)b, (uint32_t)v, ps.noise_counter, out, SCP_NOISE_ODE);
+                for (int i = 0; i < 6; ++i) { x[i] = out[6 + i]; ro.x0[iv * 6 + i] = x[i]; }
+                ro.u0[iv] = ua;
+                us[v] = ua;
+            } else {
+                for (int i = 0; i < 6; ++i) x[i] = scp_ldc(ro.x0 + iv * 6 + i, true);
+                us[v] = scp_ldc(ro.u0 + iv, true);
+            }
+            for (int i = 0; i < 6; ++i) xs[v * 6 + i] = x[i];
+            if (ro.x_hist && step == 0)
+                for (int i = 0; i < 6; ++i)
+                    ro.x_hist[(((size_t)b * (ro.nsteps + 1)) * nVeh + v) * 6 + i] = ro.mode == 1 ? scp_ldc(ro.x_meas + iv * 6 + i, true) : x[i];
+        }
+    CTA_PHASE_END
+    scp_setup_instance_at(cta, d, ps, b, xs, us, ro.veh, ro.poly, ro.ref, ro.g, ro.cterm, ro.H, ro.qv, ro.gamma0, ro.abe,
+                          ro.setup_status, red, flag, true, k1ws, k1_warps);
+}
+
+// After the SCP loop of step `step` has finished (results of the step in io.U / io.scp_iters / ...): record, close the
+// loop, account.  Returns nothing; the caller advances the step counter.
+SCP_FN void scp_rollout_advance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, const ScpRollout &ro, const ScpIO &io,
+                                int b, int step)
+{
+    const int nVeh = d.nVeh, Hp = d.Hp;
+    CTA_PHASE(tid)
+        if (ro.U_hist)
+            for (int e = tid; e < Hp * nVeh; e += cta.nt)
+                ro.U_hist[((size_t)b * ro.nsteps + step) * Hp * nVeh + e] = io.U[(size_t)b * Hp * nVeh + e];
+        for (int v = tid; v < nVeh; v += cta.nt) {
+            const size_t iv = (size_t)b * nVeh + v;
+            double x[6];
+            if (ro.mode == 1) {
+                for (int i = 0; i < 6; ++i) x[i] = scp_ldc(ro.x_meas + iv * 6 + i, true);
+                double ua = scp_ldc(ro.u_act + iv, true);
+                scp_plant_step_vehicle(x, &ua, io.U + (size_t)b * Hp * nVeh + v, (double *)0, Hp, nVeh, ro.veh[iv * 5], ro.veh[iv * 5 + 1],
+                                       ro.mech_limit, ro.lat_acc_limit, ro.duLim, p.dt, ro.nsub_plant, p.noise_sigma, p.seed,
+                                       p.instance0 + (uint32_t)b, (uint32_t)v, ro.counter0 + (uint32_t)step, (double *)0);
+                for (int i = 0; i < 6; ++i) ro.x_meas[iv * 6 + i] = x[i];
+                ro.u_act[iv] = ua;
+            } else {
+                double abe[48];
+                for (int i = 0; i < 48; ++i) abe[i] = scp_ldc(ro.abe + iv * 48 + i, true);
+                for (int i = 0; i < 6; ++i) x[i] = scp_ldc(ro.x0 + iv * 6 + i, true);
+                double u0 = scp_ldc(ro.u0 + iv, true);
+                scp_advance_vehicle(abe, io.U[(size_t)b * Hp * nVeh + v], ro.uMax, ro.duLim, x, &u0);
+                for (int i = 0; i < 6; ++i) ro.x0[iv * 6 + i] = x[i];
+                ro.u0[iv] = u0;
+            }
+            if (ro.x_hist)
+                for (int i = 0; i < 6; ++i) ro.x_hist[(((size_t)b * (ro.nsteps + 1) + step + 1) * nVeh + v) * 6 + i] = x[i];
+        }
+        if (tid == 0) {
+            const int its = io.scp_iters[b], st = io.status[b];
+            if (step == 0) { ro.qp_total[b] = 0; ro.ipm_total[b] = 0; ro.status_or[b] = 0; }
+            ro.qp_total[b] += its;
+            ro.ipm_total[b] += io.ipm_iters[b];
+            ro.status_or[b] |= st;
+            if (ro.scp_iters_hist) ro.scp_iters_hist[(size_t)b * ro.nsteps + step] = its;
+            if (ro.status_hist) ro.status_hist[(size_t)b * ro.nsteps + step] = st;
+        }
+    CTA_PHASE_END
 }
 
 // ================================================================================================ K3: dense QP

@@ -36,6 +36,7 @@ struct ScpKernelArgs {
     double *gws;
     size_t gl_stride, sh_lim;
     int alpha_slots, want_H;
+    ScpRollout ro;             // ro.nsteps > 0: the rollout entry (scpb200_mpc_rollout)
 };
 
 // what a translation unit exports per kernel instantiation
@@ -72,17 +73,45 @@ __device__ __forceinline__ int queue_pop(const WorkQueue &q)
     }
 }
 
+// One invocation of the rollout entry on instance b: (set-up if the instance is at the start of an MPC step) -> one
+// quantum of its SCP loop -> (if the loop finished: record, close the loop, next step).  Returns true when the instance
+// has run all its MPC steps.  k1ws / k1_warps: shared scratch for the warp-level set-up (the normal-matrix area, dead
+// between QPs).
+__device__ __forceinline__ bool rollout_invocation(Cta &cta, const scpb200_dims &d, const ScpKernelArgs &a, int b, ScpMem &s,
+                                                   double *k1ws, int k1_warps, int *setup_flag)
+{
+    double *stB = a.io.state + (size_t)b * SCP_STATE_W;
+    const int it_resume = (int)SCP_LD_COHERENT(stB + 2), step = (int)SCP_LD_COHERENT(stB + 7);
+    if (it_resume == 0) {
+        scp_rollout_setup(cta, d, a.p, a.ro, b, step, s.resp, s.ipm.red, setup_flag, k1ws, k1_warps);
+        __syncthreads();
+    }
+    if (!scp_solve_instance(cta, d, a.p, b, a.io, s)) return false;
+    __syncthreads();
+    scp_rollout_advance(cta, d, a.p, a.ro, a.io, b, step);
+    if (threadIdx.x == 0) {
+        stB[7] = (double)(step + 1);
+        stB[2] = 0.0;                                          // the next invocation starts a fresh SCP loop ...
+        if (!(a.p.qp_warm_start && a.p.qp_warm_carry)) stB[6] = 0.0;   // ... cold, as a new scpb200_scp_solve call would
+    }
+    return step + 1 >= a.ro.nsteps;
+}
+
 // NVEH / HP / NT > 0: literal dimensions and CTA width.  After inlining the compiler folds every index computation
 // (n, n1, tile counts, divisions by Hp, strided loops over the CTA) into constants and unrolls the short loops; in
 // its generic form the kernel executes ~20 instructions of addressing and loop control per FP64 operation.
 // MT = the unit's CTA-width bound: part of the kernel's NAME, so that the instantiations of units compiled for
 // different bounds (scp_solve_generic.cu, twice) are different symbols for the linker and the CUDA runtime.
-template <bool ALL_SHARED, int NVEH, int HP, int NT, int MT = SCP_MAX_THREADS>
+// ROLLOUT: the instantiation behind scpb200_mpc_rollout (set-up and loop closure inside the kernel).  A separate
+// instantiation, not a run-time branch: compiled into the per-step kernel the extra code cost every phase of the solver
+// 1.5x (measured), although it only runs between MPC steps.
+template <bool ALL_SHARED, int NVEH, int HP, int NT, int MT = SCP_MAX_THREADS, bool ROLLOUT = false>
 __global__ void __launch_bounds__(NT > 0 ? NT : SCP_MAX_THREADS, (NT > 0 && NT <= 128) ? 3 : (HP > 10 ? 1 : SCP_MIN_CTAS))
 k_scp_solve(const __grid_constant__ ScpKernelArgs a)
 {
     extern __shared__ double sh[];
     __shared__ int slot;
+    __shared__ int setup_flag;
     scpb200_dims d = a.d;
     if (NVEH > 0) { d.nVeh = NVEH; d.Hp = HP; d.nObst = 0; }
     const int alpha_slots = NVEH > 0 ? SCP_FIXED_ALPHA : a.alpha_slots, want_H = (NVEH > 0 && HP <= 10) ? 0 : a.want_H;
@@ -99,7 +128,17 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
         __syncthreads();
         const int b = slot;
         if (b < 0) break;
-        const bool done = scp_solve_instance(cta, d, a.p, b, a.io, s);
+        bool done;
+        if (ROLLOUT) {
+            // scratch of the warp-level set-up: the normal matrix when it is shared-resident, else the row vectors
+            const int ntile = s.ipm.T * (s.ipm.T + 1) / 2;
+            double *k1ws = ALL_SHARED ? s.ipm.S : s.ipm.bA;
+            const int k1_doubles = ALL_SHARED ? ntile * SCP_TILE2 : 8 * s.ipm.mc;
+            done = rollout_invocation(cta, d, a, b, s, k1ws, scp_imax(1, k1_doubles / SCP_K1_WARP_DOUBLES), &setup_flag);
+        } else {
+            (void)setup_flag;
+            done = scp_solve_instance(cta, d, a.p, b, a.io, s);
+        }
         __threadfence();                           // release: every thread's writes of this invocation ...
         __syncthreads();                           // ... are ordered before thread 0 hands the instance on
         if (threadIdx.x == 0) {
@@ -157,3 +196,9 @@ extern "C" const ScpKernelEntry *scp_entry_v8h20_t256(void);       // BASELINE.j
 extern "C" const ScpKernelEntry *scp_entry_v8h20_t512(void);
 extern "C" const ScpKernelEntry *scp_entry_generic_shared_wide(void);   // run-time dimensions, CTAs of up to 512 threads
 extern "C" const ScpKernelEntry *scp_entry_generic_global_wide(void);
+// the rollout instantiations (scpb200_mpc_rollout): run-time dimensions at both CTA-width bounds, and the headline shape
+extern "C" const ScpKernelEntry *scp_entry_ro_generic_shared(void);
+extern "C" const ScpKernelEntry *scp_entry_ro_generic_global(void);
+extern "C" const ScpKernelEntry *scp_entry_ro_generic_shared_wide(void);
+extern "C" const ScpKernelEntry *scp_entry_ro_generic_global_wide(void);
+extern "C" const ScpKernelEntry *scp_entry_ro_v8h10_t128(void);

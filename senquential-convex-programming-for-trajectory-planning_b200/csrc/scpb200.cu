@@ -38,8 +38,12 @@ extern "C" void scpb200_default_params(scpb200_params *p)
     p->constraint_tol = 2 * 2.1 * 1e-3;
     p->max_scp_iter = 20;
     p->obstacle_eval_mode = 0;
-    p->qp_abstol = 1e-10;
-    p->qp_reltol = 1e-10;
+    /* Stopping rule (CVXOPT's: gap <= abstol or relative gap <= reltol, residuals <= feastol) tuned to the parity bar on u:
+     * the gap bounds the distance to the minimiser, lambda_min/2 |u - u*|^2 <= gap with lambda_min = 2 R = 8000 for the
+     * reference's vehicles, so gap <= 1e-7 certifies |u - u*| <= 5e-6.  A relative rule alone does not (cost ~ 5e5 when the
+     * slack is active: relgap 1e-10 leaves 5e-5 of gap, measured |u - u*| up to 4.5e-5 on the 1024-instance workload). */
+    p->qp_abstol = 1e-7;
+    p->qp_reltol = 1e-13;
     p->qp_feastol = 1e-9;
     p->qp_dual_reg = 1e-11;
     p->inf_bound = 1e20;
@@ -101,16 +105,17 @@ static int check_dims(const scpb200_dims *d)
 #endif
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128) k_mpc_setup(scpb200_dims d, scpb200_params p, const double *x0, const double *u0,
+__global__ void __launch_bounds__(512) k_mpc_setup(scpb200_dims d, scpb200_params p, const double *x0, const double *u0,
                                                    const double *veh, const double *poly, double *ref, double *g,
                                                    double *cterm, double *H, double *qv, double *gamma0, double *abe,
                                                    int32_t *setup_status)
 {
-    __shared__ double red[SCP_RED_DOUBLES];
+    extern __shared__ double k1ws[];              // SCP_K1_WARP_DOUBLES per warp
+    __shared__ double red[2 * SCP_RED_SLOTS * 16];
     __shared__ int flag;
     Cta cta = {(int)blockDim.x};
     for (int b = blockIdx.x; b < d.B; b += gridDim.x)
-        scp_setup_instance(cta, d, p, b, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe, setup_status, red, &flag);
+        scp_setup_instance(cta, d, p, b, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe, setup_status, red, &flag, k1ws);
 }
 
 __global__ void __launch_bounds__(256) k_assemble(scpb200_dims d, scpb200_params p, const double *g, const double *cterm,
@@ -252,6 +257,7 @@ __global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_
         const int b = order ? order[i] : i;
         state[(size_t)b * SCP_STATE_W + 2] = 0.0;                  // it = 0: a fresh instance
         state[(size_t)b * SCP_STATE_W + 5] = (order && i < npinned) ? 1.0 : 0.0;
+        state[(size_t)b * SCP_STATE_W + 7] = 0.0;                  // rollout entry: MPC step the instance is at
         if (!keep_snap) state[(size_t)b * SCP_STATE_W + 6] = 0.0;    // no warm-start iterate from an earlier call
     }
     if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
@@ -570,9 +576,16 @@ extern "C" int scpb200_mpc_setup(const scpb200_dims *d, const scpb200_params *p,
     DevInfo di;
     rc = dev_info(&di);
     if (rc) return rc;
-    const int threads = 64;
-    const int grid = d->B < di.sms * 16 ? d->B : di.sms * 16;
-    k_mpc_setup<<<grid, threads, 0, (cudaStream_t)stream>>>(*d, *p, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe,
+    // the CTA width of the solve kernel: scpb200_mpc_rollout runs this set-up inside that kernel, and the order of the one
+    // reduction here (gamma0) follows the width; results of the two routes are bit-identical
+    SolvePlan pl;
+    rc = plan_scp(d, &pl);
+    if (rc) return rc;
+    const int threads = pl.threads;
+    const int grid = d->B < di.sms * 8 ? d->B : di.sms * 8;
+    const size_t k1_smem = (size_t)(threads / 32) * SCP_K1_WARP_DOUBLES * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(k_mpc_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+    k_mpc_setup<<<grid, threads, k1_smem, (cudaStream_t)stream>>>(*d, *p, x0, u0, veh, poly, ref, g, cterm, H, qv, gamma0, abe,
                                                             setup_status);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -791,9 +804,70 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     ScpKernelArgs ka;
     ka.d = *d; ka.p = *p; ka.io = io; ka.q = q; ka.gws = gws; ka.gl_stride = pl.gl_stride; ka.sh_lim = pl.sh_lim;
     ka.alpha_slots = pl.alpha_slots; ka.want_H = pl.want_H;
+    memset(&ka.ro, 0, sizeof ka.ro);
     if (pl.entry->launch(pl.grid, pl.threads, pl.smem_bytes, stream, &ka)) {
         cudaGetLastError();
         return set_err(SCPB200_ERR_CUDA, "k_scp_solve launch failed");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scpb200_mpc_rollout(const scpb200_dims *d, const scpb200_params *p, const scpb200_rollout *r, void *ws, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!p || !r || !ws) return set_err(SCPB200_ERR_ARG, "scpb200_mpc_rollout: NULL argument");
+    if (r->nsteps < 1 || (r->mode != 0 && r->mode != 1)) return set_err(SCPB200_ERR_ARG, "scpb200_mpc_rollout: nsteps >= 1, mode 0 or 1");
+    if (!r->veh || !r->poly || !r->dsafe || !r->x0 || !r->u0 || !r->ref || !r->g || !r->cterm || !r->H || !r->qv || !r->gamma0 ||
+        !r->abe || !r->u || !r->U || !r->scp_iters || !r->ipm_iters || !r->status || !r->qp_total || !r->ipm_total || !r->status_or)
+        return set_err(SCPB200_ERR_ARG, "scpb200_mpc_rollout: NULL array");
+    if (r->mode == 1 && (!r->x_meas || !r->u_act || !(r->delay > 0.0) || r->nsub_delay < 1 || r->nsub_plant < 1))
+        return set_err(SCPB200_ERR_ARG, "scpb200_mpc_rollout: mode 1 needs x_meas, u_act, delay > 0 and substep counts");
+    if (d->nObst && (!r->dsafe_obst || !r->obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
+    if (p->max_scp_iter < 1) return set_err(SCPB200_ERR_ARG, "max_scp_iter must be >= 1");
+    if (d->B == 0) return 0;
+    SolvePlan pl;
+    rc = plan_scp(d, &pl);
+    if (rc) return rc;
+    ScpIO io = {r->g, r->cterm, r->H, r->qv, r->gamma0, r->dsafe, r->dsafe_obst, r->obst, r->u, r->traj, r->U, (double *)0, r->obj,
+                r->max_violation, r->scp_iters, r->ipm_iters, r->status};
+    cudaStream_t st = (cudaStream_t)stream;
+    WorkQueue q;
+    q.hdr = (int *)ws;
+    q.cap = (int)queue_cap(d->B);
+    q.slots = (int *)((char *)ws + WS_HEADER);
+    io.state = (double *)((char *)ws + WS_HEADER + (size_t)q.cap * sizeof(int));
+    io.quantum = env_int("SCPB200_QUANTUM", 1);
+    io.snap = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
+    io.coherent = 1;
+    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d));
+    k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, (const int32_t *)0, 0, 0, q, io.state);
+    CUDA_TRY(cudaGetLastError());
+    ScpKernelArgs ka;
+    ka.d = *d; ka.p = *p; ka.io = io; ka.q = q; ka.gws = gws; ka.gl_stride = pl.gl_stride; ka.sh_lim = pl.sh_lim;
+    ka.alpha_slots = pl.alpha_slots; ka.want_H = pl.want_H;
+    ScpRollout &ro = ka.ro;
+    memset(&ro, 0, sizeof ro);
+    ro.nsteps = r->nsteps; ro.mode = r->mode; ro.counter0 = p->noise_counter;
+    ro.veh = r->veh; ro.poly = r->poly; ro.x0 = r->x0; ro.u0 = r->u0; ro.x_meas = r->x_meas; ro.u_act = r->u_act;
+    ro.ref = r->ref; ro.g = r->g; ro.cterm = r->cterm; ro.H = r->H; ro.qv = r->qv; ro.gamma0 = r->gamma0; ro.abe = r->abe;
+    ro.setup_status = r->setup_status;
+    ro.uMax = r->uMax; ro.duLim = r->duLim; ro.mech_limit = r->mech_limit; ro.lat_acc_limit = r->lat_acc_limit; ro.delay = r->delay;
+    ro.nsub_delay = r->nsub_delay; ro.nsub_plant = r->nsub_plant;
+    ro.qp_total = r->qp_total; ro.ipm_total = r->ipm_total; ro.status_or = r->status_or;
+    ro.scp_iters_hist = r->scp_iters_hist; ro.status_hist = r->status_hist; ro.U_hist = r->U_hist; ro.x_hist = r->x_hist;
+    // the rollout instantiation with the plan's working-set layout: the headline shape has its own, every other plan runs
+    // the run-time-dimension kernel of its CTA-width bound
+    const ScpKernelEntry *re;
+    if (pl.entry == scp_entry_v8h10_t128()) re = scp_entry_ro_v8h10_t128();
+    else if (pl.entry->max_threads > 256) re = pl.all_shared ? scp_entry_ro_generic_shared_wide() : scp_entry_ro_generic_global_wide();
+    else re = pl.all_shared ? scp_entry_ro_generic_shared() : scp_entry_ro_generic_global();
+    int occ = 0;
+    if (re->prepare(pl.threads, pl.smem_bytes, &occ) || occ < 1) return set_err(SCPB200_ERR_CUDA, "rollout kernel cannot be resident");
+    if (re->launch(pl.grid, pl.threads, pl.smem_bytes, stream, &ka)) {
+        cudaGetLastError();
+        return set_err(SCPB200_ERR_CUDA, "k_scp_solve (rollout) launch failed");
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -803,11 +877,13 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
 // tuning builds only: read (and clear) the per-region cycle counters
 extern "C" int scpb200_debug_read_timers(unsigned long long *out32)
 {
-    const ScpKernelEntry *es[8] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
-                                   scp_entry_v8h10_t128(), scp_entry_v8h20_t256(), scp_entry_v8h20_t512(),
-                                   scp_entry_generic_shared_wide(), scp_entry_generic_global_wide()};
+    const ScpKernelEntry *es[13] = {scp_entry_generic_shared(), scp_entry_generic_global(), scp_entry_v8h10_t256(),
+                                    scp_entry_v8h10_t128(), scp_entry_v8h20_t256(), scp_entry_v8h20_t512(),
+                                    scp_entry_generic_shared_wide(), scp_entry_generic_global_wide(),
+                                    scp_entry_ro_generic_shared(), scp_entry_ro_generic_global(), scp_entry_ro_generic_shared_wide(),
+                                    scp_entry_ro_generic_global_wide(), scp_entry_ro_v8h10_t128()};
     for (int i = 0; i < 32; ++i) out32[i] = 0;
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 13; ++e) {
         unsigned long long part[32];
         if (!es[e]->read_timers || es[e]->read_timers(part)) return set_err(SCPB200_ERR_CUDA, "timer read failed");
         for (int i = 0; i < 32; ++i) out32[i] += part[i];

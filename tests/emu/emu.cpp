@@ -160,6 +160,48 @@ extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, con
     return 0;
 }
 
+// scpb200_mpc_rollout on the host: per instance, step after step, the same device functions the kernel calls
+// (scp_rollout_setup -> scp_solve_instance -> scp_rollout_advance)
+extern "C" int emu_mpc_rollout(const scpb200_dims *d, const scpb200_params *p, int nsteps, int mode, const double *veh,
+                               const double *poly, const double *dsafe, double *x0, double *u0, double *x_meas, double *u_act,
+                               double *ref, double *g, double *cterm, double *H, double *qv, double *gamma0, double *abe,
+                               double *u, double *traj, double *U, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status,
+                               double uMax, double duLim, double mech_limit, double lat_acc_limit, double delay, int nsub_delay,
+                               int nsub_plant, int32_t *qp_total, int32_t *ipm_total, int32_t *status_or, int32_t *scp_iters_hist,
+                               int32_t *status_hist, double *U_hist, double *x_hist)
+{
+    Cta *cta = new_cta();
+    const int slots = g_alpha_slots < 0 ? g_nt / 32 : g_alpha_slots;
+    size_t shu, glu;
+    const size_t lim = (size_t)1 << 40;
+    scp_footprint(d->nVeh, d->Hp, d->nObst, slots, 1, lim, &shu, &glu);
+    std::vector<double> smem(shu + 2), gmem(glu + 2), obj(d->B), mv(d->B);
+    ScpBump bp = scp_bump(smem.data(), lim, gmem.data(), false);
+    ScpMem s;
+    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1);
+    ScpIO io = {g, cterm, H, qv, gamma0, dsafe, (const double *)0, (const double *)0, u, traj, U, (double *)0, obj.data(), mv.data(),
+                scp_iters, ipm_iters, status};
+    const size_t snapw = ipm_snap_doubles(s.ipm.n1p, s.ipm.mc);
+    std::vector<double> snapbuf((size_t)d->B * snapw, 0.0);
+    io.snap = snapbuf.data();
+    ScpRollout ro;
+    memset(&ro, 0, sizeof ro);
+    ro.nsteps = nsteps; ro.mode = mode; ro.counter0 = p->noise_counter; ro.veh = veh; ro.poly = poly; ro.x0 = x0; ro.u0 = u0;
+    ro.x_meas = x_meas; ro.u_act = u_act; ro.ref = ref; ro.g = g; ro.cterm = cterm; ro.H = H; ro.qv = qv; ro.gamma0 = gamma0;
+    ro.abe = abe; ro.uMax = uMax; ro.duLim = duLim; ro.mech_limit = mech_limit; ro.lat_acc_limit = lat_acc_limit; ro.delay = delay;
+    ro.nsub_delay = nsub_delay; ro.nsub_plant = nsub_plant; ro.qp_total = qp_total; ro.ipm_total = ipm_total; ro.status_or = status_or;
+    ro.scp_iters_hist = scp_iters_hist; ro.status_hist = status_hist; ro.U_hist = U_hist; ro.x_hist = x_hist;
+    int flag = 0;
+    for (int b = 0; b < d->B; ++b)
+        for (int step = 0; step < nsteps; ++step) {
+            scp_rollout_setup(*cta, *d, *p, ro, b, step, s.resp, s.ipm.red, &flag, (double *)0, 1);
+            scp_solve_instance(*cta, *d, *p, b, io, s);
+            scp_rollout_advance(*cta, *d, *p, ro, io, b, step);
+        }
+    free(cta);
+    return 0;
+}
+
 extern "C" int emu_ode_predict(const scpb200_dims *d, const scpb200_params *p, const double *x, const double *u_ref,
                                const double *veh, double T, int32_t steps, int32_t nsub, double *out)
 {

@@ -130,6 +130,51 @@ def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=N
     return dict(u=u, traj=traj, U=U, log=log, scp_iters=si, ipm_iters=ii, status=st, obj=obj, max_violation=mv)
 
 
+def advance_linear(abe, U, uMax, duLim, x0, u0):
+    """scpb200_advance_linear in NumPy order-preserving form (one vehicle at a time through the kernel's own function is
+    not exported; this mirrors scp_advance_vehicle exactly: clamp, then x <- Ad x + Bd u + Ed accumulated left to right)."""
+    B, nVeh = u0.shape
+    xn, un = x0.copy(), u0.copy()
+    for b in range(B):
+        for v in range(nVeh):
+            ua = min(U[b, 0, v], uMax); ua = max(ua, -uMax)
+            ua = min(ua, u0[b, v] + duLim); ua = max(ua, u0[b, v] - duLim)
+            a = abe[b, v]
+            for i in range(6):
+                acc = a[42 + i] + a[36 + i] * ua
+                for j in range(6):
+                    acc += a[i * 6 + j] * x0[b, v, j]
+                xn[b, v, i] = acc
+            un[b, v] = ua
+    return xn, un
+
+
+def mpc_rollout(x0, u0, veh, poly, dsafe, Hp, params, nsteps, uMax, duLim, u=None, x_meas=None, u_act=None, mech_limit=0.0,
+                lat_acc_limit=0.0, delay=0.0, nsub_delay=144, nsub_plant=64):
+    x0, u0, veh, poly, dsafe = _c(x0).copy(), _c(u0).copy(), _c(veh), _c(poly), _c(dsafe)
+    B, nVeh = x0.shape[0], x0.shape[1]
+    d = Dims(B, nVeh, Hp, 0, poly.shape[2])
+    n = nVeh * Hp
+    mode = 0 if x_meas is None else 1
+    xm = None if x_meas is None else _c(x_meas).copy()
+    ua = None if u_act is None else _c(u_act).copy()
+    W = dict(ref=np.zeros((B, nVeh, Hp, 2)), g=np.zeros((B, nVeh, Hp, 2)), cterm=np.zeros((B, nVeh, Hp, 2)),
+             H=np.zeros((B, nVeh, Hp, Hp)), qv=np.zeros((B, nVeh, Hp)), gamma0=np.zeros(B), abe=np.zeros((B, nVeh, 48)))
+    uu = np.zeros((B, n)) if u is None else _c(u).reshape(B, n).copy()
+    traj, U = np.zeros((B, Hp, 2, nVeh)), np.zeros((B, Hp, nVeh))
+    si, ii, st = (np.zeros(B, dtype=np.int32) for _ in range(3))
+    qt, it, so = (np.zeros(B, dtype=np.int32) for _ in range(3))
+    sh, sth = np.zeros((B, nsteps), dtype=np.int32), np.zeros((B, nsteps), dtype=np.int32)
+    Uh, xh = np.zeros((B, nsteps, Hp, nVeh)), np.zeros((B, nsteps + 1, nVeh, 6))
+    lib().emu_mpc_rollout(C.byref(d), C.byref(params), C.c_int(nsteps), C.c_int(mode), _d(veh), _d(poly), _d(dsafe), _d(x0), _d(u0),
+                          _d(xm), _d(ua), _d(W["ref"]), _d(W["g"]), _d(W["cterm"]), _d(W["H"]), _d(W["qv"]), _d(W["gamma0"]),
+                          _d(W["abe"]), _d(uu), _d(traj), _d(U), _i(si), _i(ii), _i(st), C.c_double(uMax), C.c_double(duLim),
+                          C.c_double(mech_limit), C.c_double(lat_acc_limit), C.c_double(delay), C.c_int(nsub_delay),
+                          C.c_int(nsub_plant), _i(qt), _i(it), _i(so), _i(sh), _i(sth), _d(Uh), _d(xh))
+    return dict(x0=x0, u0=u0, x_meas=xm, u_act=ua, u=uu, U=U, traj=traj, qp_total=qt, ipm_total=it, status_or=so, scp_iters_hist=sh,
+                status_hist=sth, U_hist=Uh, x_hist=xh, **W)
+
+
 def plant_step(x_meas, u_act, veh, U, mech_limit, lat_acc_limit, duLim, T, nsub, params):
     """returns (x_next, u_next, uMax, U_clamped)"""
     x, ua, veh, U = _c(x_meas).copy(), _c(u_act).copy(), _c(veh), _c(U)

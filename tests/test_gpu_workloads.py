@@ -391,3 +391,63 @@ def test_raising_max_scp_iter_after_construction_is_safe(mods):
                                   *[C.c_void_p(t.data_ptr()) for t in (bs.u, bs.traj, bs.U, bs.log, bs.scp_iters, bs.ipm_iters,
                                                                        bs.status, bs.obj, bs.max_violation, bs.ws)], None)
     assert rc == -1 and b"log_capacity" in bs.lib.scpb200_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ rollout entry
+def test_rollout_is_bit_identical_to_the_per_step_calls(mods):
+    """scpb200_mpc_rollout (all MPC steps of every instance in one launch, instances re-queued across steps) against the
+    per-step sequence setup -> solve -> advance_linear with the same noise counters: every step's controller output,
+    QP count and status, the final state and warm start, bit for bit."""
+    torch, scen = mods["torch"], mods["scen"]
+    B, nsteps = 300, 5
+    cb = scen.circle_batch(B, nVeh=8, Hp=10, step_lo=4, step_hi=7)
+    def fresh():
+        bs = mods["batch"].BatchSCP(B, 8, 10, params=_params(mods, noise_sigma=3e-6, seed=11, noise_counter=2))
+        bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, 80)))
+        return bs
+    a = fresh()
+    R = a.rollout(nsteps, scen.MECH_LIMIT, scen.DU_LIM, history=True)
+    torch.cuda.synchronize()
+    b = fresh()
+    for s in range(nsteps):
+        np.testing.assert_array_equal(host(R["x_hist"])[:, s], host(b.x0))
+        b.params.noise_counter = 2 + s
+        b.setup()
+        b.solve()
+        np.testing.assert_array_equal(host(R["scp_iters_hist"])[:, s], host(b.scp_iters))
+        np.testing.assert_array_equal(host(R["status_hist"])[:, s], host(b.status))
+        np.testing.assert_array_equal(host(R["U_hist"])[:, s], host(b.U))
+        b.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+    for k in ("x0", "u0", "u", "U", "traj", "g", "H", "qv", "gamma0"):
+        np.testing.assert_array_equal(host(getattr(a, k)), host(getattr(b, k)), err_msg=k)
+    assert (host(R["qp_total"]) == host(R["scp_iters_hist"]).sum(axis=1)).all()
+    assert int(host(R["qp_total"]).sum()) > B * nsteps
+
+
+def test_rollout_with_the_plant_equals_mpc_step(mods):
+    """mode 1: delay compensation -> set-up -> SCP -> clamp + plant integration inside the kernel, against BatchSCP.mpc_step."""
+    torch, scen = mods["torch"], mods["scen"]
+    R0 = load_golden("circle8_hp10_run.npz")
+    G0 = load_golden("circle8_hp10_step0.npz")
+    B, nsteps = 6, 8
+    mech, lat, du, dt = (float(R0[k]) for k in ("sc_mechanicalSteeringLimit", "sc_lateralAccelerationLimit", "sc_duLim", "sc_dt"))
+    delay = float(R0["sc_delay_x"]) + dt + float(R0["sc_delay_u"])
+    def fresh():
+        bs = make_batch(mods, G0, B=B, noise_sigma=3e-6, seed=5)
+        x = torch.as_tensor(np.repeat(R0["sc_x_init"][None], B, 0).copy()).cuda()
+        ua = torch.as_tensor(np.repeat(R0["sc_u_init"][None], B, 0).copy()).cuda()
+        return bs, x, ua
+    a, xa, ua = fresh()
+    R = a.rollout(nsteps, mech, du, x_meas=xa, u_act=ua, mech_limit=mech, lat_acc_limit=lat, delay=delay, nsub_delay=144,
+                  nsub_plant=64, history=True)
+    torch.cuda.synchronize()
+    b, xb, ub = fresh()
+    for s in range(nsteps):
+        b.params.noise_counter = s
+        b.mpc_step(xb, ub, mech, lat, du, delay)
+        np.testing.assert_array_equal(host(R["scp_iters_hist"])[:, s], host(b.scp_iters))
+        np.testing.assert_array_equal(host(R["U_hist"])[:, s], host(b.U))
+        np.testing.assert_array_equal(host(R["x_hist"])[:, s + 1], host(xb))
+    np.testing.assert_array_equal(host(xa), host(xb))
+    np.testing.assert_array_equal(host(ua), host(ub))
+    assert np.abs(host(xa)[0] - host(xa)[1]).max() > 0.0          # instances draw different noise

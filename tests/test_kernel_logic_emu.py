@@ -152,7 +152,9 @@ def test_dense_qp_kernel_long_horizon_size(oracle, nt, reverse, force_global):
     b = rng.uniform(0.1, 1.0, mc)
     lb, ub = -np.full(n1, 0.4), np.full(n1, 0.4)
     emu.config(nt=nt, reverse=reverse, force_global_S=force_global)
-    r = emu.qp_solve_dense(P[None], q[None], A[None], b[None], lb[None], ub[None], capi.default_params_py())
+    prm = capi.default_params_py()
+    prm.qp_abstol = prm.qp_reltol = 1e-10         # the defaults are tuned to the SCP QP's curvature (R = 4000); this P is O(1)
+    r = emu.qp_solve_dense(P[None], q[None], A[None], b[None], lb[None], ub[None], prm)
     o = oracle.qp_boxed(P, q, A, b, lb, ub, opts=dict(abstol=1e-10, reltol=1e-10, feastol=1e-9))
     assert o["status"] == 0 and (r["status"][0] & ~capi.ST_QP_DRES_FLOOR) == 0, (o["status"], r["status"][0])
     assert np.abs(r["x"][0] - o["x"]).max() < 1e-7
@@ -369,3 +371,31 @@ def test_frog_scenario_obstacle_rows_vs_reference(oracle, fname, reverse):
     assert r["scp_iters"][0] == nit
     assert np.abs(r["u"][0] - G["u_final"]).max() < 1e-6
     assert np.abs(r["traj"][0] - G["Traj"]).max() < 1e-4
+
+
+def test_rollout_equals_the_step_by_step_call_sequence():
+    """scpb200_mpc_rollout's per-instance logic (set-up inside the solve kernel, loop closure, step accounting) against
+    the per-step entry points: setup -> solve -> advance on the linear model, three MPC steps, bit for bit."""
+    scen = importlib.import_module("senquential-convex-programming-for-trajectory-planning_b200.scenarios")
+    cb = scen.circle_batch(3, nVeh=8, Hp=10, step_lo=5, step_hi=6)
+    p = capi.default_params_py()
+    p.noise_sigma, p.seed, p.noise_counter = 3e-6, 77, 4
+    nsteps = 3
+    R = emu.mpc_rollout(cb.x0, cb.u0, cb.veh, cb.poly, cb.dsafe, 10, p, nsteps, scen.MECH_LIMIT, scen.DU_LIM)
+    x0, u0, u = cb.x0.copy(), cb.u0.copy(), np.zeros((3, 80))
+    for s in range(nsteps):
+        q = capi.default_params_py()
+        q.noise_sigma, q.seed, q.noise_counter = 3e-6, 77, 4 + s
+        S = emu.mpc_setup(x0, u0, cb.veh, cb.poly, 10, q)
+        O = emu.scp_solve(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], cb.dsafe, u, q)
+        np.testing.assert_array_equal(R["scp_iters_hist"][:, s], O["scp_iters"])
+        np.testing.assert_array_equal(R["status_hist"][:, s], O["status"])
+        np.testing.assert_array_equal(R["U_hist"][:, s], O["U"])
+        np.testing.assert_array_equal(R["x_hist"][:, s], x0)
+        x0, u0 = emu.advance_linear(S["abe"], O["U"], scen.MECH_LIMIT, scen.DU_LIM, x0, u0)
+        u = O["u"]
+    np.testing.assert_array_equal(R["x0"], x0)
+    np.testing.assert_array_equal(R["u0"], u0)
+    np.testing.assert_array_equal(R["u"], u)
+    np.testing.assert_array_equal(R["x_hist"][:, nsteps], x0)
+    assert (R["qp_total"] == R["scp_iters_hist"].sum(axis=1)).all() and (R["qp_total"] >= nsteps).all()

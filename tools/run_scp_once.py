@@ -31,6 +31,7 @@ ap.add_argument("--warm-relgap", dest="wrg", type=float, default=-1.0)
 ap.add_argument("--snap-min-iter", dest="smi", type=int, default=0)
 ap.add_argument("--carry", type=int, default=0)
 ap.add_argument("--warm-max-iter", dest="wmi", type=int, default=0)
+ap.add_argument("--rollout", type=int, default=0, help="run the steps as ONE scpb200_mpc_rollout launch")
 args = ap.parse_args()
 
 cb = scen.circle_batch(args.batch, Hp=args.hp, step_lo=args.step_lo, step_hi=args.step_hi)
@@ -49,7 +50,13 @@ bs = batch.BatchSCP(args.batch, 8, args.hp, params=p)
 bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((args.batch, 8 * args.hp)))
 print("plan", bs.plan())
 TOT_IPM = TOT_QP = 0
-for s in range(args.steps):
+if args.rollout:
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record(); R = bs.rollout(args.steps, scen.MECH_LIMIT, scen.DU_LIM); e[1].record()
+    torch.cuda.synchronize()
+    TOT_QP, TOT_IPM = int(R["qp_total"].sum()), int(R["ipm_total"].sum())
+    print(f"rollout of {args.steps} steps: {e[0].elapsed_time(e[1]):.3f} ms ({e[0].elapsed_time(e[1]) / args.steps:.3f} per step), QPs {TOT_QP}, IPM its {TOT_IPM}")
+for s in range(0 if args.rollout else args.steps):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record(); bs.setup(); e[1].record(); bs.solve(); e[2].record()
     torch.cuda.synchronize()
