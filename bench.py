@@ -62,6 +62,14 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def fp64_peak():
+    """FP64 peak of this pool's B200 from the committed measurement (profiles/fp64_peak.json, written from
+    tools/microbench_dmma.cu / tools/microbench.cu runs): MEASURED_PEAKS.json carries no FP64 entry."""
+    with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+        d = json.load(f)
+    return float(d["dmma_tflops"]), d["source"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -149,7 +157,9 @@ def run_reference(args):
         return
     scen = importlib.import_module(PKG + ".scenarios")
     cores = os.cpu_count() or 1
-    Bs = args.cpu_sample
+    # the product arm's own configuration: the same `batch` instances (global ids 0 .. batch-1, i.e. rank 0's shard), the same
+    # closed-loop MPC steps; --cpu-sample B overrides (the product arm's cpu_baseline leg uses a smaller sample)
+    Bs = args.cpu_sample if args.cpu_sample > 0 else args.batch
     opts = dict(abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100)        # CVXOPT's documented defaults
     qps, sec, ipm = cpu_controller_run(Bs, args.nveh, args.hp, args.steps, args.warmup, 0, cores, opts, args.noise_sigma,
                                        args.seed, scen.MECH_LIMIT, scen.DU_LIM, args.step_lo, args.step_hi)
@@ -158,10 +168,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, Bs, note="bounded sample of the product arm's workload on the host cores"),
+        "config": workload_config(args, Bs),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{Bs} instances x {args.steps} closed-loop MPC steps ({qps} QPs, {ipm} IPM iterations), "
-                                   f"oracle coneqp restatement at CVXOPT default tolerances, {cores} threads"},
+                                   f"oracle coneqp restatement (C) at CVXOPT default tolerances 1e-7/1e-6/1e-7 (looser than the "
+                                   f"product arm's), {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -173,8 +184,7 @@ def workload_config(args, B_per_gpu, note=None):
                        f"perturbed instances with process noise sigma={args.noise_sigma} (Monte-Carlo), closed-loop MPC steps "
                        f"starting at step U{{{args.step_lo}..{args.step_hi}}} (BASELINE.json configs[1])",
            "nVeh": args.nveh, "Hp": args.hp, "batch_per_gpu": B_per_gpu, "n1": args.nveh * args.hp + 1,
-           "mc": args.hp * args.nveh * (args.nveh - 1) // 2, "l2": "flushed between timed steps (256 MiB write)",
-           "qp_tolerances": {"abstol": 1e-10, "reltol": 1e-10, "feastol": 1e-9}}
+           "mc": args.hp * args.nveh * (args.nveh - 1) // 2, "l2": "flushed between timed steps (256 MiB write)"}
     if getattr(args, "trust_frac", 0) > 0:
         cfg["trust_radius"] = f"{args.trust_frac} * uLim"
     if getattr(args, "max_scp_iter", 0) > 0:
@@ -198,6 +208,101 @@ def ncu_traffic(kernel, args=None):
         return None
 
 
+def strong_leg(args, mods, dev, rank, world, flush, barrier, total=4096):
+    """The north-star configuration (BASELINE.json: a 4096-scenario batch over the GPUs of the box): `total` instances in
+    all, rank r owns the contiguous shard parallel.shard_range(total, r, world); the same closed-loop MPC steps, timed per
+    step with CUDA events (L2 flushed), summed per rank.  Returns (seconds on this rank, QPs, IPM iterations, shard size)."""
+    import torch
+    capi, batch, scen, par = mods
+    lo, hi = par.shard_range(total, rank, world)
+    B = hi - lo
+    cb = scen.circle_batch(B, nVeh=args.nveh, Hp=args.hp, instance0=lo, step_lo=args.step_lo, step_hi=args.step_hi)
+    p = capi.Params()
+    capi.load().scpb200_default_params(C.byref(p))
+    p.noise_sigma, p.seed, p.instance0 = args.noise_sigma, args.seed, lo
+    if args.trust_frac > 0:
+        p.trust_radius = args.trust_frac * p.uLim
+    if args.max_scp_iter > 0:
+        p.max_scp_iter = args.max_scp_iter
+    bs = batch.BatchSCP(B, args.nveh, args.hp, params=p, device=dev, keep_log=False)
+    bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, args.nveh * args.hp)))
+    uMax, duLim = scen.MECH_LIMIT, scen.DU_LIM
+    for s in range(args.warmup):
+        bs.params.noise_counter = s
+        bs.setup(); bs.solve(); bs.advance_linear(uMax, duLim)
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        e0[k].record()
+        bs.params.noise_counter = args.warmup + k
+        bs.setup(); bs.solve(); bs.advance_linear(uMax, duLim)
+        e1[k].record()
+        cnt += torch.stack([bs.scp_iters.sum(), bs.ipm_iters.sum()])
+    barrier()
+    ms = [e0[k].elapsed_time(e1[k]) for k in range(args.steps)]
+    asm_frac = None
+    if rank == 0 and not args.skip_assembly:                # the assembly kernel at this shard size (north star: >= 60 % of HBM)
+        out = bs.assemble_dense()
+        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+        for i in range(3):
+            bs.assemble_dense_into(bs.u, out)
+        for i in range(10):
+            flush.zero_()
+            a0[i].record(); bs.assemble_dense_into(bs.u, out); a1[i].record()
+        torch.cuda.synchronize(dev)
+        ams = float(np.mean([a0[i].elapsed_time(a1[i]) for i in range(10)]))
+        peaks, _ = measured_peaks()
+        asm_frac = assembly_bytes_per_qp(args.nveh, args.hp) * B / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"]
+        del out
+    c = cnt.cpu()
+    return float(np.sum(ms)) * 1e-3, int(c[0]), int(c[1]), B, float(np.median(ms)), asm_frac
+
+
+def sharding_check(args, mods, dev, rank, world, nsample=64, nsteps=2):
+    """Bit-identity of per-instance results across shards, on the hardware: rank r solves `nsample` instances of its OWN shard
+    and the first `nsample` of rank (r+1) % world's shard (as a batch of its own, at other batch positions, on another
+    GPU); SHA-256 of (U, u, traj, scp_iters, ipm_iters, status) after `nsteps` closed-loop MPC steps must agree.  At
+    world = 1 the second batch is the same instances at shifted batch positions (instances 32 .. 32+nsample)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    capi, batch, scen, par = mods
+    B = args.batch
+
+    def digest(i0, n):
+        cb = scen.circle_batch(n, nVeh=args.nveh, Hp=args.hp, instance0=i0, step_lo=args.step_lo, step_hi=args.step_hi)
+        p = capi.Params()
+        capi.load().scpb200_default_params(C.byref(p))
+        p.noise_sigma, p.seed, p.instance0 = args.noise_sigma, args.seed, i0
+        bs = batch.BatchSCP(n, args.nveh, args.hp, params=p, device=dev, keep_log=False)
+        bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((n, args.nveh * args.hp)))
+        for s in range(nsteps):
+            bs.params.noise_counter = s
+            bs.setup(); bs.solve(); bs.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+        torch.cuda.synchronize(dev)
+        return [hashlib.sha256(b"".join(getattr(bs, k)[i].cpu().numpy().tobytes() for k in
+                                        ("U", "u", "traj", "scp_iters", "ipm_iters", "status"))).hexdigest() for i in range(n)]
+
+    if world == 1:
+        a, b = digest(0, nsample), digest(nsample // 2, nsample)
+        same = a[nsample // 2:] == b[: nsample - nsample // 2]
+        return {"ok": bool(same), "instances_compared": nsample - nsample // 2,
+                "how": "one GPU: the same global instances solved at two different batch positions, SHA-256 per instance"}
+    own = digest(rank * B, nsample)
+    nxt = digest(((rank + 1) % world) * B, nsample)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (own, nxt))
+    ok = all(gathered[r][1] == gathered[(r + 1) % world][0] for r in range(world))
+    return {"ok": bool(ok), "instances_compared": nsample * world,
+            "how": f"rank r re-solved the first {nsample} instances of rank (r+1) % N's shard on its own GPU; SHA-256 per instance of "
+                   f"U, u, traj, iteration counts and status after {nsteps} closed-loop MPC steps, all-gathered and compared"}
+
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -211,6 +316,8 @@ def run_product(args):
     capi = importlib.import_module(PKG + "._capi")
     batch = importlib.import_module(PKG + ".batch")
     scen = importlib.import_module(PKG + ".scenarios")
+    par = importlib.import_module(PKG + ".parallel")
+    mods = (capi, batch, scen, par)
     B, nVeh, Hp = args.batch, args.nveh, args.hp
     inst0 = rank * B                                        # weak scaling: B instances per rank, disjoint global ids
     cb = scen.circle_batch(B, nVeh=nVeh, Hp=Hp, instance0=inst0, step_lo=args.step_lo, step_hi=args.step_hi)
@@ -276,6 +383,7 @@ def run_product(args):
     launches = bs.kernel_launches - launches0
     step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)])
     solve_ms = np.array([evs0[k].elapsed_time(evs1[k]) for k in range(args.steps)])
+    setup_ms = np.array([ev0[k].elapsed_time(evs0[k]) for k in range(args.steps)])
     t_dev = float(step_ms.sum()) * 1e-3
     qps_rank = int(qp_counts.sum().item())
     ipm_rank = int(ipm_counts.sum().item())
@@ -353,18 +461,25 @@ def run_product(args):
                "unit": "GB/s", "frac": abytes / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": ncu_traffic("k_assemble", args),
                "peak_source": how,
                "ms_per_launch": ams, "algorithmic_bytes_per_launch": abytes}
+        if asm["traffic"]:                                  # DRAM-level: bytes that reached HBM inside the launch (ncu capture) / time
+            asm["frac_dram"] = asm["traffic"] / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"]
         del outbuf
+
+    # ---------------- north-star strong configuration + sharding bit-identity ----------------
+    st_t, st_qps, st_ipm, st_B, st_p50, st_asm = strong_leg(args, mods, dev, rank, world, flush, barrier, total=args.strong_total)
+    shard = sharding_check(args, mods, dev, rank, world)
 
     # ---------------- reduce over ranks ----------------
     t_max, qps_all, e2e_max, e2e_all = t_dev, qps_rank, t_e2e, e2e_qps
+    st_t_max, st_qps_all, st_ipm_all = st_t, st_qps, st_ipm
     roll_t_max, roll_qps_all, roll_ipm_all = t_roll, roll_qps, roll_ipm
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e, t_roll], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_dev, t_e2e, t_roll, st_t], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank, roll_qps, roll_ipm], dtype=torch.int64, device=dev)
+        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank, roll_qps, roll_ipm, st_qps, st_ipm], dtype=torch.int64, device=dev)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        t_max, e2e_max, roll_t_max = float(tt[0]), float(tt[1]), float(tt[2])
-        qps_all, e2e_all, ipm_all, roll_qps_all, roll_ipm_all = (int(v) for v in cc)
+        t_max, e2e_max, roll_t_max, st_t_max = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
+        qps_all, e2e_all, ipm_all, roll_qps_all, roll_ipm_all, st_qps_all, st_ipm_all = (int(v) for v in cc)
         # the optional all-gather of trajectories / statistics, off the timed path
         gathered = [torch.empty_like(bs.U) for _ in range(world)]
         dist.all_gather(gathered, bs.U)
@@ -379,7 +494,15 @@ def run_product(args):
         # around the launch on its stream.
         fl = fit * ipm_per_step
         ach = float(fl.sum() / (solve_ms.sum() * 1e-3) / 1e12)
-        fp64_peak = float(os.environ.get("SCPB200_FP64_PEAK_TFLOPS", "37.0"))
+        fp64_pk, fp64_src = fp64_peak()
+        # K1 (set-up): bytes in + out per instance over the CUDA-event time of its launch
+        k1_bytes = sum(getattr(bs, k).numel() * 8 for k in ("x0", "u0", "veh", "poly", "ref", "g", "cterm", "H", "qv", "gamma0", "abe"))
+        peaks_, how_ = measured_peaks()
+        k1_ach = k1_bytes / (float(setup_ms.mean()) * 1e-3) / 1e9
+        setup_roof = {"bound": "hbm", "kernel": "k_mpc_setup", "achieved": k1_ach, "peak": peaks_["hbm_gbs"], "unit": "GB/s",
+                      "frac": k1_ach / peaks_["hbm_gbs"], "ms_per_launch": float(setup_ms.mean()), "algorithmic_bytes_per_launch": k1_bytes,
+                      "share_of_step": float(setup_ms.sum() / step_ms.sum()), "peak_source": how_,
+                      "note": "latency-bound at this batch (one warp per vehicle, 8x8 Pade products on DMMA); bytes = inputs + every K1 output"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -389,15 +512,23 @@ def run_product(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe: DMMA m8n8k4 (the FP64 tensor path) and DFMA share one "
                          "peak on B200; the kernel is latency / issue bound far below it (DESIGN.md section 4)",
-                         "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak, "traffic": ncu_traffic("k_scp_solve", args),
-                         "peak_source": "measured on this pool's B200 (tools/microbench_dmma.cu: DMMA m8n8k4 37.0 TFLOP/s, "
-                                        "DFMA 36.5; profiles/r01_microbench*.txt); MEASURED_PEAKS.json has no FP64 entry",
+                         "kernel": "k_scp_solve", "achieved": ach, "peak": fp64_pk, "unit": "TFLOP/s",
+                         "frac": ach / fp64_pk, "traffic": ncu_traffic("k_scp_solve", args),
+                         "peak_source": "profiles/fp64_peak.json: " + fp64_src,
                          "algorithmic_flops_per_ipm_iteration": fit, "solve_share_of_step": float(solve_ms.sum() / step_ms.sum())},
             "roofline_assembly": asm,
+            "roofline_setup": setup_roof,
+            "north_star_strong": {"value": st_qps_all / st_t_max, "unit": UNIT, "batch_total": args.strong_total,
+                                  "batch_per_gpu": st_B, "ms_per_step": 1e3 * st_t_max / args.steps, "p50_ms_per_mpc_step_rank0": st_p50,
+                                  "scaling": "strong", "qps_total": st_qps_all, "ipm_iterations_total": st_ipm_all,
+                                  "roofline_frac": float(fit * st_ipm_all / world / st_t_max / 1e12 / fp64_pk),
+                                  "assembly_frac_hbm_rank0": st_asm,
+                                  "note": "BASELINE.json north star: 4096 scenarios in total, contiguous shards of 4096/N per GPU, the same "
+                                          "closed-loop MPC steps (max over ranks of the summed CUDA-event step times)"},
+            "sharding_bitwise_ok": shard,
             "rollout": {"value": roll_qps_all / roll_t_max, "unit": UNIT, "ms_per_step": 1e3 * roll_t_max / args.steps,
                         "steps_per_launch": args.steps, "qps_total": roll_qps_all, "ipm_iterations_total": roll_ipm_all,
-                        "roofline_frac": float(fit * roll_ipm_all / world / roll_t_max / 1e12 / fp64_peak),
+                        "roofline_frac": float(fit * roll_ipm_all / world / roll_t_max / 1e12 / fp64_pk),
                         "note": "scpb200_mpc_rollout: the same closed-loop workload with all timed MPC steps of every instance in one "
                                 "launch (instances re-queued across steps inside the kernel); bit-identical results, no per-step tail"},
             "stats": {"qps_total": qps_all, "ipm_iterations_total": ipm_all, "qp_per_instance_step": qps_all / (world * B * args.steps),
@@ -408,13 +539,18 @@ def run_product(args):
                       "plan": bs.plan()},
         }
         if not args.skip_cpu and world == 1:                   # the CPU baseline is reported at N = 1 only
-            cores = os.cpu_count() or 1
-            opts = dict(abstol=1e-7, reltol=1e-6, feastol=1e-7, maxiters=100)
-            cq, cs, ci = cpu_controller_run(args.cpu_sample, nVeh, Hp, args.steps, 0, 0, cores, opts, args.noise_sigma, args.seed,
-                                            uMax, duLim, args.step_lo, args.step_hi)
-            line["cpu_baseline"] = {"value": cq / cs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} instances x {args.steps} closed-loop MPC steps ({cq} QPs), oracle "
-                                              f"coneqp restatement at CVXOPT default tolerances (1e-7/1e-6/1e-7), {cores} threads"}
+            # in a child process: the product arm's own process never imports, links or maps anything under oracle/
+            sample = args.cpu_sample if args.cpu_sample > 0 else 256
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.steps), "--warmup", "0",
+                   "--cpu-sample", str(sample), "--batch", str(B), "--hp", str(Hp), "--nveh", str(nVeh),
+                   "--noise-sigma", str(args.noise_sigma), "--seed", str(args.seed), "--step-lo", str(args.step_lo),
+                   "--step-hi", str(args.step_hi)]
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=900).stdout.strip().splitlines()
+                line["cpu_baseline"] = json.loads(out[-1])["cpu_baseline"]
+            except Exception as e:                              # report, do not fail the product line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": f"child process failed: {e!r}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -434,10 +570,13 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--step-lo", dest="step_lo", type=int, default=4)
     ap.add_argument("--step-hi", dest="step_hi", type=int, default=7)
-    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=256, help="instances of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=0,
+                    help="instances of the CPU run (0: --impl reference runs the product arm's full batch; the cpu_baseline leg 256)")
     ap.add_argument("--trust-radius-frac", dest="trust_frac", type=float, default=0.0,
                     help="BASELINE configs[3]: trust region |u - ubar|_inf <= frac * uLim folded into the box (0 = off, the reference)")
     ap.add_argument("--max-scp-iter", dest="max_scp_iter", type=int, default=0, help="SCP iteration cap (0 = the reference's 20)")
+    ap.add_argument("--strong-total", dest="strong_total", type=int, default=4096,
+                    help="total instances of the north-star strong-scaling leg (sharded over the ranks)")
     ap.add_argument("--skip-cpu", dest="skip_cpu", action="store_true")
     ap.add_argument("--skip-assembly", dest="skip_assembly", action="store_true")
     args = ap.parse_args()
