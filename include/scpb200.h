@@ -96,8 +96,10 @@ typedef struct scpb200_params {
     /* extension: steering-rate rows inside the QP (the reference only clamps AFTER the solve, main.py:144-174).
      * With enable_rate_rows = 1 every QP carries, per vehicle v and step k, the two rows
      *     u_v[k] - u_v[k-1] <= duLim,   u_v[k-1] - u_v[k] <= duLim        (u_v[-1] = u_prev[v], the command being actuated)
-     * appended after the collision / obstacle rows in the order (v, k, +), (v, k, -): mc grows by 2 nVeh Hp.
-     * Default 0 reproduces the reference bit for bit. */
+     * (row order of the equivalent dense QP: after the collision / obstacle rows, (v, k, +), (v, k, -); 2 nVeh Hp rows).
+     * Inside K4 they are never materialised: two non-zeros per row make them a tridiagonal term of every vehicle block of
+     * the normal matrix.  u_prev comes in through scpb200_scp_solve_rate (per-step entry) or is the set-up input u0
+     * (scpb200_mpc_rollout).  Default 0 reproduces the reference bit for bit (same kernels, same layout). */
     int32_t enable_rate_rows;
     int32_t log_capacity;    /* rows per instance allocated in the `log` array of scpb200_scp_solve (0: max_scp_iter rows);
                               * a call with max_scp_iter > log_capacity > 0 is rejected instead of writing past the rows */
@@ -257,6 +259,19 @@ int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_params *p, co
                               const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
                               double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
                               double *max_violation, const int32_t *order, void *ws, void *stream);
+
+/*
+ * K4 with steering-rate rows (north-star item 2, "input/rate-bound constraint rows"; no reference counterpart: the
+ * reference clamps the solved command afterwards, main.py:164-174, so its QP can ask for a steering step the actuator
+ * will not deliver).  As scpb200_scp_solve_ordered, plus
+ *   u_prev[B,nVeh]   the command being actuated (Iter.u0, MPC_Iter.py:19): anchors the first rate row of every vehicle.
+ * Required when p->enable_rate_rows != 0 (the other two entries then fail with SCPB200_ERR_ARG); ignored otherwise.
+ */
+int scpb200_scp_solve_rate(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                           const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                           const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                           double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                           double *max_violation, const int32_t *order, const double *u_prev, void *ws, void *stream);
 
 /*
  * Rollout entry (north-star item 4: "the SCP ... loop kept on-device with noise injection for Monte-Carlo rollouts") —

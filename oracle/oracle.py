@@ -235,6 +235,15 @@ def qp_boxed(P, q, A, b, lb, ub, opts=None, inf_bound=1e20, quad=False):
                 pres=info[4], dres=info[5], iterations=int(info[6]))
 
 
+def rate_rows(nVeh, Hp, u_prev, duLim):
+    """Dense steering-rate rows of the product's `enable_rate_rows` extension (include/scpb200.h): A[2n, n1], b[2n] in the
+    order (v, k, +), (v, k, -)."""
+    n = nVeh * Hp
+    A, b = np.empty((2 * n, n + 1)), np.empty(2 * n)
+    lib().orc_rate_rows(C.c_int(nVeh), C.c_int(Hp), _p(_c(u_prev).ravel()), C.c_double(duLim), _p(A), _p(b))
+    return A, b
+
+
 def stack_G(A, b, lb, ub, inf_bound=1e20):
     """G=[Aineq; I; -I], h=[bineq; ub; -lb] with infinite bounds dropped, as orc_qp_boxed builds it."""
     n1 = A.shape[1]
@@ -248,8 +257,9 @@ def stack_G(A, b, lb, ub, inf_bound=1e20):
 def scp_optimizer(g, cterm, H, qv, gamma0, dsafe, u, dsafeExtra=1.0, uLim=3 * np.pi / 180, delta_tol=1e-3,
                   omega_weight=1e5, omega_ub=1e25, constraint_tol=2 * 2.1 * 1e-3, max_scp_iter=20,
                   trust_radius=np.inf, opts=None, inf_bound=1e20, dsafe_obst=None, obst=None, obstacle_mode=0,
-                  quad=False):
-    """One instance of SCP_optimizer (SCP_controller.py:74-197).  Returns dict(u, feasible, obj, iters, log, u_hist)."""
+                  quad=False, u_prev=None, duLim=0.0):
+    """One instance of SCP_optimizer (SCP_controller.py:74-197).  Returns dict(u, feasible, obj, iters, log, u_hist).
+    u_prev[nVeh] (with duLim): the product's steering-rate-row extension (rate_rows below) in every QP."""
     g = _c(g)
     nVeh, Hp = g.shape[0], g.shape[1]
     nObst, dso, ob = _obst_args(nVeh, Hp, dsafe_obst, obst)
@@ -262,12 +272,13 @@ def scp_optimizer(g, cterm, H, qv, gamma0, dsafe, u, dsafeExtra=1.0, uLim=3 * np
     obj = C.c_double(0)
     o = _opts(opts)
     tr = 1e308 if not np.isfinite(trust_radius) else float(trust_radius)
-    its = lib().orc_scp_optimizer(
+    up = None if u_prev is None else _c(u_prev).ravel()
+    its = lib().orc_scp_optimizer_rate(
         C.c_int(nVeh), C.c_int(Hp), C.c_int(nObst), _p(g), _p(_c(cterm)), _p(_c(H)), _p(_c(qv)), C.c_double(gamma0),
         _p(_c(dsafe)), _p(dso), _p(ob), C.c_double(dsafeExtra), C.c_double(uLim), C.c_double(delta_tol),
         C.c_double(omega_weight), C.c_double(omega_ub), C.c_double(constraint_tol), C.c_int(max_scp_iter),
         C.c_double(tr), C.c_int(obstacle_mode), C.byref(o), C.c_double(inf_bound), C.c_int(int(quad)), _p(u),
-        C.byref(feas), C.byref(obj), _p(log), _p(uh))
+        C.byref(feas), C.byref(obj), _p(log), _p(uh), None if up is None else _p(up), C.c_double(duLim))
     return dict(u=u, feasible=bool(feas.value), obj=obj.value, iters=its, log=log[:its], u_hist=uh[:its])
 
 

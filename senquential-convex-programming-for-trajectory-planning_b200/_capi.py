@@ -86,6 +86,7 @@ PROTOTYPES = {
     "scpb200_qp_solve_dense": [C.POINTER(Dims), C.POINTER(Params), C.c_int32, C.c_int32] + [_P] * 13,
     "scpb200_scp_solve": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 19,
     "scpb200_scp_solve_ordered": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 20,
+    "scpb200_scp_solve_rate": [C.POINTER(Dims), C.POINTER(Params)] + [_P] * 21,
     "scpb200_work_order": [C.c_int32, _P, _P, _P],
     "scpb200_mpc_rollout": [C.POINTER(Dims), C.POINTER(Params), C.POINTER(Rollout), _P, _P],
 }

@@ -149,12 +149,14 @@ class BatchSCP:
                       "scpb200_work_order")
                 self.kernel_launches += 1
                 order = self.order
-            check(self.lib.scpb200_scp_solve_ordered(
+            # u0 (the command being actuated, the set-up's input) anchors the steering-rate rows when they are enabled
+            check(self.lib.scpb200_scp_solve_rate(
                 C.byref(self.dims), C.byref(self.params), _ptr(self.g), _ptr(self.cterm), _ptr(self.H), _ptr(self.qv),
                 _ptr(self.gamma0), _ptr(self.dsafe), _ptr(self.dsafe_obst), _ptr(self.obst), _ptr(self.u),
                 _ptr(self.traj), _ptr(self.U), _ptr(self.log), _ptr(self.scp_iters), _ptr(self.ipm_iters),
-                _ptr(self.status), _ptr(self.obj), _ptr(self.max_violation), _ptr(order), _ptr(self.ws), self._stream()),
-                "scpb200_scp_solve_ordered")
+                _ptr(self.status), _ptr(self.obj), _ptr(self.max_violation), _ptr(order),
+                _ptr(self.u0) if self.params.enable_rate_rows else None, _ptr(self.ws), self._stream()),
+                "scpb200_scp_solve_rate")
         self.kernel_launches += 2          # k_queue_init + k_scp_solve
         self._have_work = True
 

@@ -48,7 +48,15 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()
     objdir = os.path.join(OBJ, tag)
     os.makedirs(objdir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, d) for d in DEPS if d.endswith((".cuh", ".h"))]
     for obj, src, extra in UNITS:
+        # per-unit staleness: an object is rebuilt when its own source or any header is newer (objects of other variants,
+        # i.e. other `defines`, live in their own directory)
+        op = os.path.join(objdir, obj)
+        if not force and os.path.exists(op) and not verbose:
+            t = os.path.getmtime(op)
+            if all(os.path.getmtime(f) <= t for f in headers + [os.path.join(CSRC, src)]):
+                continue
         cmd = ["nvcc"] + NVCC_FLAGS + list(defines) + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", "-o", os.path.join(objdir, obj), os.path.join(CSRC, src)]
         procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))

@@ -57,6 +57,15 @@ struct IpmMem {
     double *ub, *sU, *zU, *dsU, *dzU, *ccU, *eU;         // [n1p]   x <= ub rows
     double *lb, *sL, *zL, *dsL, *dzL, *ccL, *eL;         // [n1p]   x >= lb rows
     double *dinv;   // [n1p]             reciprocal pivots of the factor
+    // difference rows (steering-rate bounds, params.enable_rate_rows): for c < nr, with the difference operator
+    //     (D x)[c] = x[c] - (c % rper ? x[c-1] : 0)      (rper = Hp: the chain restarts at every vehicle)
+    // the two rows  (D x)[c] <= hP[c]  and  -(D x)[c] <= hM[c].  Like the box rows they never enter A: they add a
+    // tridiagonal term to the vehicle blocks of the normal matrix (diagonal through dgf, sub-diagonal through rsub).
+    // nr = 0: none (a compile-time zero in the fixed-shape kernels, so every loop below folds away).
+    int nr, rper;
+    double *hP, *sP, *zP, *dsP, *dzP, *ccP, *eP;         // [nr]
+    double *hM, *sM, *zM, *dsM, *dzM, *ccM, *eM;         // [nr]
+    double *rsub;   // [nr]              S[c][c-1] += rsub[c]  (0 where the chain restarts)
     double *red;    // [SCP_RED_DOUBLES] reduction scratch (double-buffered, see scp_common.cuh)
     double *t8;     // [16] tile-solve scratch (8) + flags
 };
@@ -71,7 +80,20 @@ struct IpmResult {
 // (n1p - 1) carries a right-hand side through the factorisation (see chol_factor).
 SCP_HDFN int ipm_padded(int n1) { return scp_round_up(n1 + 1, SCP_TILE); }
 
-SCP_HDFN size_t ipm_snap_doubles(int n1p, int mc) { return (size_t)5 * n1p + 2 * (size_t)((mc + 1) & ~1); }
+SCP_HDFN size_t ipm_snap_doubles(int n1p, int mc, int nr = 0)
+{
+    return (size_t)5 * n1p + 2 * (size_t)((mc + 1) & ~1) + 4 * (size_t)((nr + 1) & ~1);
+}
+
+// difference rows: (D x)[c], and column c of D' w for w = wP - wM
+SCP_FN bool ipm_rfirst(const IpmMem &m, int c) { return c % m.rper == 0; }
+SCP_FN double ipm_rdiff(const IpmMem &m, const double *x, int c) { return x[c] - (ipm_rfirst(m, c) ? 0.0 : x[c - 1]); }
+SCP_FN double ipm_rcol(const IpmMem &m, const double *wP, const double *wM, int c)
+{
+    double a = wP[c] - wM[c];
+    if (c + 1 < m.nr && !ipm_rfirst(m, c + 1)) a -= wP[c + 1] - wM[c + 1];
+    return a;
+}
 
 // Copy the interior iterate (x, sA, zA, sU, zU, sL, zL) to / from the snapshot area (one phase).
 SCP_FN void ipm_snapshot(Cta &cta, const IpmMem &m, double *snap, bool save)
@@ -80,13 +102,20 @@ SCP_FN void ipm_snapshot(Cta &cta, const IpmMem &m, double *snap, bool save)
     const size_t rows = (size_t)((mc + 1) & ~1);
     double *px = snap, *psA = px + n1p, *pzA = psA + rows, *psU = pzA + rows, *pzU = psU + n1p, *psL = pzU + n1p,
            *pzL = psL + n1p;
+    const size_t rr = (size_t)((m.nr + 1) & ~1);
+    double *psP = pzL + n1p, *pzP = psP + rr, *psM = pzP + rr, *pzM = psM + rr;
     CTA_PHASE(tid)
         if (save) {
+            for (int c = tid; c < m.nr; c += cta.nt) { psP[c] = m.sP[c]; pzP[c] = m.zP[c]; psM[c] = m.sM[c]; pzM[c] = m.zM[c]; }
             for (int c = tid; c < n1p; c += cta.nt) {
                 px[c] = m.x[c]; psU[c] = m.sU[c]; pzU[c] = m.zU[c]; psL[c] = m.sL[c]; pzL[c] = m.zL[c];
             }
             for (int r = tid; r < mc; r += cta.nt) { psA[r] = m.sA[r]; pzA[r] = m.zA[r]; }
         } else {
+            for (int c = tid; c < m.nr; c += cta.nt) {
+                m.sP[c] = SCP_LD_COHERENT(psP + c); m.zP[c] = SCP_LD_COHERENT(pzP + c);
+                m.sM[c] = SCP_LD_COHERENT(psM + c); m.zM[c] = SCP_LD_COHERENT(pzM + c);
+            }
             for (int c = tid; c < n1p; c += cta.nt) {
                 m.x[c] = SCP_LD_COHERENT(px + c);
                 m.sU[c] = SCP_LD_COHERENT(psU + c); m.zU[c] = SCP_LD_COHERENT(pzU + c);
@@ -503,6 +532,21 @@ SCP_FN void ipm_pass_rhs(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, i
             if (pass == 1) bs -= m.ccA[r];
             m.dzA[r] = ipm_w1(s, z, m.rzA[r], m.eA[r], bs);                       // w1 in dzA
         }
+        for (int c = tid; c < m.nr; c += cta.nt) {
+            const double df = ipm_rdiff(m, m.x, c);
+            {
+                const double s = m.sP[c], z = m.zP[c];
+                double bs = smu - s * z;
+                if (pass == 1) bs -= m.ccP[c];
+                m.dzP[c] = ipm_w1(s, z, s + df - m.hP[c], m.eP[c], bs);
+            }
+            {
+                const double s = m.sM[c], z = m.zM[c];
+                double bs = smu - s * z;
+                if (pass == 1) bs -= m.ccM[c];
+                m.dzM[c] = ipm_w1(s, z, s - df - m.hM[c], m.eM[c], bs);
+            }
+        }
     CTA_PHASE_END
     op.prep(cta, (const double *)0, m.dzA);
     // rhs = -rx - G'w1
@@ -510,6 +554,7 @@ SCP_FN void ipm_pass_rhs(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, i
         for (int c = tid; c < n1p; c += cta.nt) {
             double rhs = 0.0;
             if (c < n1) rhs = -m.rx[c] - op.col_dot(c);
+            if (c < m.nr) rhs -= ipm_rcol(m, m.dzP, m.dzM, c);
             if (ipm_has_ub(m, ctl, c)) {
                 const double s = m.sU[c], z = m.zU[c];
                 double bs = smu - s * z;
@@ -555,6 +600,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
             if (ipm_has_lb(m, ctl, c)) { cnt += 1.0; hh += m.lb[c] * m.lb[c]; }
         }
         for (int r = tid; r < mc; r += cta.nt) hh += m.bA[r] * m.bA[r];
+        for (int c = tid; c < m.nr; c += cta.nt) { cnt += 2.0; hh += m.hP[c] * m.hP[c] + m.hM[c] * m.hM[c]; }
         CTA_RED_SUM(cta, red, 0, tid, cnt)
         CTA_RED_SUM(cta, red, 1, tid, hq)
         CTA_RED_SUM(cta, red, 2, tid, hh)
@@ -573,14 +619,21 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
             for (int c = tid; c < n1p; c += cta.nt) {
                 double rhs = 0.0;
                 if (c < n1) rhs = op.col_dot(c) - m.q[c];
+                if (c < m.nr) rhs += ipm_rcol(m, m.hP, m.hM, c);
                 if (ipm_has_ub(m, ctl, c)) rhs += m.ub[c];
                 if (ipm_has_lb(m, ctl, c)) rhs += m.lb[c];
                 m.x[c] = rhs;
             }
         CTA_PHASE_END
         op.form_normal(cta, m, m.dsA, m.tn, m.x, [](int) { return 1.0; },                    // dd = 1
-                       [&](int c) { return (ipm_has_ub(m, ctl, c) ? 1.0 : 0.0) + (ipm_has_lb(m, ctl, c) ? 1.0 : 0.0); }
-                       SCP_TIMER_PASS);
+                       [&](int c) {
+                           double d = (ipm_has_ub(m, ctl, c) ? 1.0 : 0.0) + (ipm_has_lb(m, ctl, c) ? 1.0 : 0.0);
+                           if (c < m.nr) {                                                // D'D of both difference rows
+                               d += 2.0 + ((c + 1 < m.nr && !ipm_rfirst(m, c + 1)) ? 2.0 : 0.0);
+                               m.rsub[c] = ipm_rfirst(m, c) ? 0.0 : -2.0;
+                           }
+                           return d;
+                       } SCP_TIMER_PASS);
         SCP_TIMER(1)
         chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
         chol_invert_diag(cta, m, m.x);
@@ -594,6 +647,12 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                 const double z = op.row_dot(r) - m.bA[r];
                 m.zA[r] = z; m.sA[r] = -z;
                 nrm += z * z; ts = fmax(ts, z); tz = fmax(tz, -z);
+            }
+            for (int c = tid; c < m.nr; c += cta.nt) {
+                const double df = ipm_rdiff(m, m.x, c);
+                const double zp = df - m.hP[c], zm = -df - m.hM[c];
+                m.zP[c] = zp; m.sP[c] = -zp; m.zM[c] = zm; m.sM[c] = -zm;
+                nrm += zp * zp + zm * zm; ts = fmax(ts, fmax(zp, zm)); tz = fmax(tz, fmax(-zp, -zm));
             }
             for (int c = tid; c < n1p; c += cta.nt) {
                 if (ipm_has_ub(m, ctl, c)) {
@@ -619,6 +678,9 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
         }
         CTA_PHASE(tid)
             for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += as_shift; m.zA[r] += az_shift; }
+            for (int c = tid; c < m.nr; c += cta.nt) {
+                m.sP[c] += as_shift; m.zP[c] += az_shift; m.sM[c] += as_shift; m.zM[c] += az_shift;
+            }
             for (int c = tid; c < n1p; c += cta.nt) {
                 if (ipm_has_ub(m, ctl, c)) { m.sU[c] += as_shift; m.zU[c] += az_shift; }
                 if (ipm_has_lb(m, ctl, c)) { m.sL[c] += as_shift; m.zL[c] += az_shift; }
@@ -641,6 +703,20 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                     const double px = op.P_col(c, m.x);
                     pf += m.x[c] * (0.5 * px + m.q[c]);
                     r = px + m.q[c] + op.col_dot(c);
+                }
+                if (c < m.nr) {
+                    r += ipm_rcol(m, m.zP, m.zM, c);
+                    const double df = ipm_rdiff(m, m.x, c);
+                    {
+                        const double s = m.sP[c], z = m.zP[c], rz = s + df - m.hP[c];
+                        pg += s * z; prz += rz * rz; pzr += z * rz;
+                        m.eP[c] = 1.0 / (s + ctl.dual_reg * z);
+                    }
+                    {
+                        const double s = m.sM[c], z = m.zM[c], rz = s - df - m.hM[c];
+                        pg += s * z; prz += rz * rz; pzr += z * rz;
+                        m.eM[c] = 1.0 / (s + ctl.dual_reg * z);
+                    }
                 }
                 if (ipm_has_ub(m, ctl, c)) {
                     const double s = m.sU[c], z = m.zU[c], rz = s + m.x[c] - m.ub[c];
@@ -704,6 +780,12 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                            double d = 0.0;
                            if (ipm_has_ub(m, ctl, c)) d += m.zU[c] * m.eU[c];
                            if (ipm_has_lb(m, ctl, c)) d += m.zL[c] * m.eL[c];
+                           if (c < m.nr) {                          // D' diag(dP + dM) D: tridiagonal inside a vehicle block
+                               const double tc = m.zP[c] * m.eP[c] + m.zM[c] * m.eM[c];
+                               d += tc;
+                               if (c + 1 < m.nr && !ipm_rfirst(m, c + 1)) d += m.zP[c + 1] * m.eP[c + 1] + m.zM[c + 1] * m.eM[c + 1];
+                               m.rsub[c] = ipm_rfirst(m, c) ? 0.0 : -tc;
+                           }
                            return d;
                        } SCP_TIMER_PASS);
         SCP_TIMER(1)
@@ -735,6 +817,31 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                     m.dzA[r] = dz; m.dsA[r] = ds;
                     pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
                     if (pass == 0) m.ccA[r] = ds * dz;
+                }
+                for (int c = tid; c < m.nr; c += cta.nt) {
+                    const double gdx = ipm_rdiff(m, m.dx, c);
+                    {
+                        const double s = m.sP[c], z = m.zP[c];
+                        double bs = smu - s * z;
+                        if (pass == 1) bs -= m.ccP[c];
+                        const double pinv = 1.0 / (s * z);
+                        const double dz = m.dzP[c] + z * m.eP[c] * gdx;
+                        const double ds = (bs - s * dz) * (pinv * s);
+                        m.dzP[c] = dz; m.dsP[c] = ds;
+                        pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
+                        if (pass == 0) m.ccP[c] = ds * dz;
+                    }
+                    {
+                        const double s = m.sM[c], z = m.zM[c];
+                        double bs = smu - s * z;
+                        if (pass == 1) bs -= m.ccM[c];
+                        const double pinv = 1.0 / (s * z);
+                        const double dz = m.dzM[c] - z * m.eM[c] * gdx;
+                        const double ds = (bs - s * dz) * (pinv * s);
+                        m.dzM[c] = dz; m.dsM[c] = ds;
+                        pdd += ds * dz; ts = fmax(ts, -ds * (pinv * z)); tz = fmax(tz, -dz * (pinv * s));
+                        if (pass == 0) m.ccM[c] = ds * dz;
+                    }
                 }
                 for (int c = tid; c < n1p; c += cta.nt) {
                     if (ipm_has_ub(m, ctl, c)) {
@@ -781,6 +888,10 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                 if (ipm_has_lb(m, ctl, c)) { m.sL[c] += step * m.dsL[c]; m.zL[c] += step * m.dzL[c]; }
             }
             for (int r = tid; r < mc; r += cta.nt) { m.sA[r] += step * m.dsA[r]; m.zA[r] += step * m.dzA[r]; }
+            for (int c = tid; c < m.nr; c += cta.nt) {
+                m.sP[c] += step * m.dsP[c]; m.zP[c] += step * m.dzP[c];
+                m.sM[c] += step * m.dsM[c]; m.zM[c] += step * m.dzM[c];
+            }
         CTA_PHASE_END
     }
     if (*fixed_p) status |= SCPB200_ST_QP_PIVOT;

@@ -203,7 +203,8 @@ struct PairOp {
     // A[a = l>>2][kappa] = g_v[k-a][c] and B[kappa][b = l>>2] = (M_v(k) g_v[k-b])[c] (two multiply-adds from the
     // aggregated 2x2 blocks), and owns C[a = l>>2][b = 2(l&3), 2(l&3)+1].  Causality skips the kappa-steps below the tile
     // row: Hp = 10 needs 7 DMMAs per vehicle (the entry-by-entry loop it replaces was ~40 % of form_normal).
-    SCP_MFN void diag_block_mma(int lane, double *S, int v, const double *dg) const
+    // rsub (or null): sub-diagonal additions of the difference rows, S[(v,a),(v,a-1)] += rsub[v*Hp + a].
+    SCP_MFN void diag_block_mma(int lane, double *S, int v, const double *dg, const double *rsub) const
     {
         const double *gv = g + (size_t)v * Hp * 2;
         const double *Mv = Msm + (size_t)v * Hp * 3;
@@ -228,6 +229,10 @@ struct PairOp {
                 }
                 const int b0 = 8 * tb + 2 * kq;
                 if (a < Hp) {
+                    if (rsub) {
+                        if (a == b0 + 1) c0 += rsub[v * Hp + a];
+                        if (a == b0 + 2) c1 += rsub[v * Hp + a];
+                    }
                     if (b0 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0)] = c0 + 2.0 * scp_ldc(Hv + a * Hp + b0, coh) + (a == b0 ? dg[v * Hp + a] : 0.0);
                     if (b0 + 1 <= a) S[scp_sidx(v * Hp + a, v * Hp + b0 + 1)] = c1 + 2.0 * scp_ldc(Hv + a * Hp + b0 + 1, coh) + (a == b0 + 1 ? dg[v * Hp + a] : 0.0);
                 }
@@ -243,6 +248,7 @@ struct PairOp {
                         const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;
                         acc += gv[(k - a) * 2] * bx + gv[(k - a) * 2 + 1] * by;
                     }
+                    if (rsub && a == b + 1) acc += rsub[v * Hp + a];
                     S[scp_sidx(v * Hp + a, v * Hp + b)] = acc + 2.0 * scp_ldc(Hv + a * Hp + b, coh) + (a == b ? dg[v * Hp + a] : 0.0);
                 }
 #endif
@@ -266,6 +272,7 @@ struct PairOp {
     SCP_MFN void form_normal(Cta &cta, const Mem &m, double *dd, double *dg, const double *rhs_row, DD ddf, DG dgf SCP_TIMER_ARG)
     {
         double *S = m.S;
+        const double *rsub = m.nr > 0 ? m.rsub : (const double *)0;     // written by dgf in phase 1, read in phase 2
         CTA_RED_BEGIN(cta, 1)
         CTA_PHASE(tid)
             double sw = 0.0;
@@ -317,7 +324,7 @@ struct PairOp {
                             while (q >= nVeh - 1 - i) { q -= nVeh - 1 - i; ++i; }
                             pair_block_mma(lane, S, i, i + 1 + q, p * Hp, dd);
                         } else {
-                            diag_block_mma(lane, S, p - npair, dg);
+                            diag_block_mma(lane, S, p - npair, dg, rsub);
                         }
                     }
                 WARP_PHASE_END
@@ -343,6 +350,7 @@ struct PairOp {
                 const double *gv = g + (size_t)v * Hp * 2;
                 const double *Mv = Msm + (size_t)v * Hp * 3;
                 double acc = 2.0 * scp_ldc(H + ((size_t)v * Hp + a) * Hp + b, coh) + (a == b ? dg[v * Hp + a] : 0.0);
+                if (rsub && a == b + 1) acc += rsub[v * Hp + a];
                 for (int k = a; k < Hp; ++k) {
                     const double gbx = gv[(k - b) * 2], gby = gv[(k - b) * 2 + 1];
                     const double bx = Mv[k * 3] * gbx + Mv[k * 3 + 1] * gby, by = Mv[k * 3 + 1] * gbx + Mv[k * 3 + 2] * gby;

@@ -842,9 +842,11 @@ SCP_HDFN ScpBump scp_bump(double *sh, size_t sh_lim, double *gl, bool all_shared
 // carved last by ipm_carve_big so that they are the first to overflow.
 // red_doubles: size of the per-warp reduction scratch of the kernel that will run on this layout (SCP_RED_DOUBLES of
 // ITS translation unit: units compiled for wider CTAs carry more warps)
-SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles = SCP_RED_DOUBLES)
+// nr: difference (steering-rate) rows, 0 = none (the layout without them is unchanged)
+SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles = SCP_RED_DOUBLES, int nr = 0, int rper = 1)
 {
     m.n1 = n1; m.n1p = ipm_padded(n1); m.T = m.n1p / SCP_TILE; m.mc = mc;
+    m.nr = nr; m.rper = rper > 0 ? rper : 1;
     m.red = bp.take((size_t)red_doubles);
     m.t8 = bp.take(16);
     m.x = bp.take(m.n1p); m.q = bp.take(m.n1p); m.rx = bp.take(m.n1p); m.dx = bp.take(m.n1p); m.tn = bp.take(m.n1p);
@@ -864,6 +866,15 @@ SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles 
 #endif
     }
     m.eA = bp.take(mc);
+    if (nr > 0) {
+        m.hP = bp.take(nr); m.sP = bp.take(nr); m.zP = bp.take(nr); m.dsP = bp.take(nr); m.dzP = bp.take(nr); m.ccP = bp.take(nr); m.eP = bp.take(nr);
+        m.hM = bp.take(nr); m.sM = bp.take(nr); m.zM = bp.take(nr); m.dsM = bp.take(nr); m.dzM = bp.take(nr); m.ccM = bp.take(nr); m.eM = bp.take(nr);
+        m.rsub = bp.take(nr);
+    } else {
+        m.hP = m.sP = m.zP = m.dsP = m.dzP = m.ccP = m.eP = 0;
+        m.hM = m.sM = m.zM = m.dsM = m.dzM = m.ccM = m.eM = 0;
+        m.rsub = 0;
+    }
 }
 
 SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
@@ -883,10 +894,10 @@ struct ScpMem {
 // want_H: keep a shared-memory copy of the instance's cost blocks (read every iteration); otherwise they are read
 // from global memory.
 SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int alpha_slots, int want_H,
-                        int red_doubles = SCP_RED_DOUBLES)
+                        int red_doubles = SCP_RED_DOUBLES, int rate_rows = 0)
 {
     const int n = nVeh * Hp, mc = Hp * (nVeh * (nVeh - 1) / 2 + nVeh * nObst);
-    ipm_carve(bp, s.ipm, n + 1, mc, red_doubles);
+    ipm_carve(bp, s.ipm, n + 1, mc, red_doubles, rate_rows ? n : 0, Hp);
     s.g = bp.take((size_t)n * 2);
     s.dbar = bp.take((size_t)mc * 2);
     s.resp = bp.take((size_t)n * 2);
@@ -905,11 +916,11 @@ SCP_HDFN void scp_carve(ScpBump &bp, ScpMem &s, int nVeh, int Hp, int nObst, int
 
 // total doubles of the working set / split under a shared-memory limit (host-side planning)
 SCP_HDFN void scp_footprint(int nVeh, int Hp, int nObst, int alpha_slots, int want_H, size_t sh_lim, size_t *sh_used,
-                            size_t *gl_used, int red_doubles = SCP_RED_DOUBLES)
+                            size_t *gl_used, int red_doubles = SCP_RED_DOUBLES, int rate_rows = 0)
 {
     ScpBump bp = scp_bump(0, sh_lim, 0, false);
     ScpMem s;
-    scp_carve(bp, s, nVeh, Hp, nObst, alpha_slots, want_H, red_doubles);
+    scp_carve(bp, s, nVeh, Hp, nObst, alpha_slots, want_H, red_doubles, rate_rows);
     *sh_used = bp.sh_off;
     *gl_used = bp.gl_off;
 }
@@ -936,6 +947,8 @@ struct ScpIO {
     int quantum;
     double *snap;       // [B][ipm_snap_doubles] interior-point warm-start iterates, or null (every QP starts cold)
     int coherent;       // the set-up outputs (g, cterm, H, qv, gamma0) were written during this launch: read them past L1
+    const double *u_prev;   // [B][nVeh] command being actuated (Iter.u0): anchors the first steering-rate row of every
+                            // vehicle; read only when params.enable_rate_rows (then required)
 };
 #define SCP_STATE_W 8   /* obj0, mv0, it, ipm_total, status bits, pinned (never parked), snapshot valid, (spare) */
 
@@ -960,7 +973,7 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     ctl.abstol = p.qp_abstol; ctl.reltol = p.qp_reltol; ctl.feastol = p.qp_feastol;
     ctl.dual_reg = p.qp_dual_reg; ctl.inf_bound = p.inf_bound; ctl.max_iter = p.ipm_max_iter;
     ctl.dres_floor = p.qp_dres_floor_factor * p.qp_feastol;
-    ctl.snap = (io.snap && p.qp_warm_start) ? io.snap + (size_t)b * ipm_snap_doubles(m.n1p, mc) : 0;
+    ctl.snap = (io.snap && p.qp_warm_start) ? io.snap + (size_t)b * ipm_snap_doubles(m.n1p, mc, m.nr) : 0;
     ctl.snap_relgap = p.qp_warm_relgap;
     ctl.warm = 0;
     ctl.snap_min_iter = p.qp_warm_min_iter;
@@ -970,7 +983,8 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
     op.nVeh = nVeh; op.Hp = Hp; op.n = n; op.nObst = nObst; op.mcv = mcv; op.mc = mc;
     op.g = s.g; op.H = s.H_local ? s.Hs : HB; op.dbar = s.dbar; op.resp = s.resp; op.frc = s.frc; op.red = m.red;
     op.xom = 0.0; op.wsum = 0.0;
-    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots; op.rowtab = s.rowtab; op.coh = coh;
+    op.Msm = s.Msm; op.alpha_slots = s.alpha_slots; op.rowtab = s.rowtab;
+    op.coh = coh && !s.H_local;      // the operator reads H only: past L1 when it is the global array another CTA wrote, plainly from the shared copy
 
     double *stB = io.state ? io.state + (size_t)b * SCP_STATE_W : 0;
     const int it_resume = stB ? (int)SCP_LD_COHERENT(stB + 2) : 0;       // > 0: a parked instance
@@ -1036,6 +1050,14 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
                 } else if (c == n) { lo = 0.0; hi = p.omega_ub; }
                 m.lb[c] = lo;
                 m.ub[c] = hi;
+            }
+            // steering-rate rows (extension; the reference clamps after the solve, main.py:164-174):
+            // |u_v[k] - u_v[k-1]| <= duLim with u_v[-1] = the command being actuated
+            for (int c = tid; c < m.nr; c += cta.nt) {
+                const int v = c / Hp;
+                const double up = (c - v * Hp == 0) ? SCP_LD_COHERENT(io.u_prev + (size_t)b * nVeh + v) : 0.0;
+                m.hP[c] = p.duLim + up;
+                m.hM[c] = p.duLim - up;
             }
         CTA_PHASE_END
         IpmResult res;

@@ -118,7 +118,9 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
     Cta cta = {NT > 0 ? NT : (int)blockDim.x};
     ScpBump bp = scp_bump(sh, a.sh_lim, ALL_SHARED ? (double *)0 : a.gws + (size_t)blockIdx.x * a.gl_stride, ALL_SHARED);
     ScpMem s;
-    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H);
+    // steering-rate rows: run-time-dimension instantiations only (a literal 0 folds every rate-row loop out of the others)
+    const int rate_rows = NVEH > 0 ? 0 : (a.p.enable_rate_rows != 0);
+    scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H, SCP_RED_DOUBLES, rate_rows);
     for (;;) {
         if (threadIdx.x == 0) {
             const int b = queue_pop(a.q);

@@ -338,11 +338,11 @@ static size_t queue_bytes(long B)
     return (b + 255) & ~(size_t)255;
 }
 // bytes of the interior-point warm-start iterates (one per instance)
-static size_t snap_bytes(const scpb200_dims *d)
+static size_t snap_bytes(const scpb200_dims *d, int rate_rows)
 {
     const int n1p = ipm_padded(d->nVeh * d->Hp + 1);
     const int mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
-    const size_t b = (size_t)(d->B < 1 ? 1 : d->B) * ipm_snap_doubles(n1p, mc) * sizeof(double);
+    const size_t b = (size_t)(d->B < 1 ? 1 : d->B) * ipm_snap_doubles(n1p, mc, rate_rows ? d->nVeh * d->Hp : 0) * sizeof(double);
     return (b + 255) & ~(size_t)255;
 }
 #define SCP_SM_SHARED_BYTES 233472      /* 228 KiB per SM on B200, 1 KiB reserved per resident CTA */
@@ -395,6 +395,41 @@ static int plan_common(KS kshared, KG kglobal, FP footprint, int max_ctas, int B
 }
 
 static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl);
+
+// The dynamic shared-memory limit is an attribute of the kernel FUNCTION, and several plans share one function (the
+// run-time-dimension instantiations serve every shape, with and without steering-rate rows): planning one shape leaves
+// the attribute at that shape's size.  Plans are cached, so a launch cannot rely on its own planning pass having been the
+// last one: every prepare() goes through here and records what the function's limit currently is; launches re-prepare
+// when it is not theirs (one table lookup per launch otherwise).
+struct AttrSlot { const ScpKernelEntry *e; int dev; size_t smem; };
+static AttrSlot g_attr[64];
+static int g_attr_count = 0;
+static std::mutex g_attr_mutex;
+static int entry_prepare(const ScpKernelEntry *e, int threads, size_t smem, int *occ)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    const int rc = e->prepare(threads, smem, occ);
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    int hit = -1;
+    for (int i = 0; i < g_attr_count; ++i)
+        if (g_attr[i].e == e && g_attr[i].dev == dev) { hit = i; break; }
+    if (hit < 0) hit = g_attr_count < 64 ? g_attr_count++ : 0;
+    g_attr[hit].e = e; g_attr[hit].dev = dev; g_attr[hit].smem = rc ? (size_t)-1 : smem;
+    return rc;
+}
+static int entry_ensure(const ScpKernelEntry *e, int threads, size_t smem)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        for (int i = 0; i < g_attr_count; ++i)
+            if (g_attr[i].e == e && g_attr[i].dev == dev && g_attr[i].smem == smem) return 0;
+    }
+    int occ = 0;
+    return entry_prepare(e, threads, smem, &occ) || occ < 1;
+}
 // rate rows change the working-set layout (mc grows by 2n): part of the plan key, set by the entry points before planning
 static thread_local int g_plan_rate_rows = 0;
 
@@ -492,7 +527,7 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
         const ScpKernelEntry *ks = wide ? scp_entry_generic_shared_wide() : scp_entry_generic_shared();
         const ScpKernelEntry *kg = wide ? scp_entry_generic_global_wide() : scp_entry_generic_global();
         // the fixed-shape instantiations cover the layout without shared-resident cost blocks
-        if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && nObst == 0 && slots == 1) {
+        if (env_int("SCPB200_SPECIALISE", 1) && nVeh == 8 && nObst == 0 && slots == 1 && !g_plan_rate_rows) {
             if (Hp == 10 && threads == 256 && want_H == 0) ks = scp_entry_v8h10_t256();
             else if (Hp == 10 && threads == 128 && want_H == 0) ks = scp_entry_v8h10_t128();
             else if (Hp == 20 && threads == 256) ks = scp_entry_v8h20_t256();          // either placement of the cost blocks
@@ -500,9 +535,12 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
         }
         const int red_doubles = 2 * SCP_RED_SLOTS * (ks->max_threads / 32);
         if (kg->max_threads != ks->max_threads) return set_err(SCPB200_ERR_ARG, "internal: kernel units of one plan differ in CTA-width bound");
-        auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu, red_doubles); };
+        const int rate = g_plan_rate_rows;
+        auto fp = [=](size_t lim, size_t *shu, size_t *glu) { scp_footprint(nVeh, Hp, nObst, slots, want_H, lim, shu, glu, red_doubles, rate); };
         SolvePlan cand = *pl;
-        int rc = plan_common(ks->prepare, kg->prepare, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand, ks->max_threads);
+        auto prep_s = [ks](int t, size_t sm, int *o) { return entry_prepare(ks, t, sm, o); };
+        auto prep_g = [kg](int t, size_t sm, int *o) { return entry_prepare(kg, t, sm, o); };
+        int rc = plan_common(prep_s, prep_g, fp, env_int("SCPB200_MAX_CTAS", 4), d->B, &cand, ks->max_threads);
         if (rc) return rc;
         cand.want_H = want_H;
         cand.entry = cand.all_shared ? ks : kg;
@@ -511,7 +549,7 @@ static int plan_scp_threads(const scpb200_dims *d, int threads, SolvePlan *pl)
     *pl = best;
     // plan_common leaves the function attributes of the last candidate: set them for the chosen one
     int occ = 0;
-    if (pl->entry->prepare(pl->threads, pl->smem_bytes, &occ)) return set_err(SCPB200_ERR_CUDA, "kernel attribute query failed");
+    if (entry_prepare(pl->entry, pl->threads, pl->smem_bytes, &occ)) return set_err(SCPB200_ERR_CUDA, "kernel attribute query failed");
     return 0;
 }
 
@@ -539,16 +577,22 @@ extern "C" int scpb200_workspace_bytes(const scpb200_dims *d, size_t *bytes)
     int rc = check_dims(d);
     if (rc) return rc;
     if (!bytes) return set_err(SCPB200_ERR_ARG, "bytes is NULL");
-    SolvePlan a, b;
+    SolvePlan a, a_rate, b;
     scpb200_dims dd = *d;
     if (dd.B < 1) dd.B = 1;
     dd.B = 1 << 30;                                   // size for a full grid regardless of B
+    g_plan_rate_rows = 0;
     rc = plan_scp(&dd, &a);
     if (rc) return rc;
+    g_plan_rate_rows = 1;                             // the workspace serves calls with and without steering-rate rows
+    rc = plan_scp(&dd, &a_rate);
+    g_plan_rate_rows = 0;
+    if (rc) return rc;
+    if (a_rate.ws_bytes > a.ws_bytes) a.ws_bytes = a_rate.ws_bytes;
     const int n1 = d->nVeh * d->Hp + 1, mc = d->Hp * (d->nVeh * (d->nVeh - 1) / 2 + d->nVeh * d->nObst);
     rc = plan_qp(n1, mc, 1 << 30, &b);
     if (rc) return rc;
-    *bytes = (a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes) + queue_bytes(d->B) + snap_bytes(d);
+    *bytes = (a.ws_bytes > b.ws_bytes ? a.ws_bytes : b.ws_bytes) + queue_bytes(d->B) + snap_bytes(d, 1);
     return 0;
 }
 
@@ -579,7 +623,9 @@ extern "C" int scpb200_mpc_setup(const scpb200_dims *d, const scpb200_params *p,
     // the CTA width of the solve kernel: scpb200_mpc_rollout runs this set-up inside that kernel, and the order of the one
     // reduction here (gamma0) follows the width; results of the two routes are bit-identical
     SolvePlan pl;
+    g_plan_rate_rows = p->enable_rate_rows != 0;
     rc = plan_scp(d, &pl);
+    g_plan_rate_rows = 0;
     if (rc) return rc;
     const int threads = pl.threads;
     const int grid = d->B < di.sms * 8 ? d->B : di.sms * 8;
@@ -775,6 +821,17 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
                                          int32_t *ipm_iters, int32_t *status, double *obj, double *max_violation,
                                          const int32_t *order, void *ws, void *stream)
 {
+    return scpb200_scp_solve_rate(d, p, g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, scp_iters,
+                                  ipm_iters, status, obj, max_violation, order, (const double *)0, ws, stream);
+}
+
+extern "C" int scpb200_scp_solve_rate(const scpb200_dims *d, const scpb200_params *p, const double *g,
+                                      const double *cterm, const double *H, const double *qv, const double *gamma0,
+                                      const double *dsafe, const double *dsafe_obst, const double *obst,
+                                      double *u_inout, double *traj, double *U, double *log, int32_t *scp_iters,
+                                      int32_t *ipm_iters, int32_t *status, double *obj, double *max_violation,
+                                      const int32_t *order, const double *u_prev, void *ws, void *stream)
+{
     int rc = check_dims(d);
     if (rc) return rc;
     if (!p || !g || !cterm || !H || !qv || !gamma0 || !dsafe || !u_inout || !ws)
@@ -783,12 +840,19 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     if (p->max_scp_iter < 1) return set_err(SCPB200_ERR_ARG, "max_scp_iter must be >= 1");
     if (log && p->log_capacity > 0 && p->max_scp_iter > p->log_capacity)
         return set_err(SCPB200_ERR_ARG, "scpb200_scp_solve: max_scp_iter exceeds log_capacity (rows allocated per instance in log)");
+    const int rate = p->enable_rate_rows != 0;
+    if (rate && !u_prev)
+        return set_err(SCPB200_ERR_ARG, "enable_rate_rows needs u_prev (the command being actuated): call scpb200_scp_solve_rate");
+    if (rate && !(p->duLim > 0.0)) return set_err(SCPB200_ERR_ARG, "enable_rate_rows needs duLim > 0");
     if (d->B == 0) return 0;
     SolvePlan pl;
+    g_plan_rate_rows = rate;
     rc = plan_scp(d, &pl);
+    g_plan_rate_rows = 0;
     if (rc) return rc;
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
+    io.u_prev = u_prev;
     cudaStream_t st = (cudaStream_t)stream;
     WorkQueue q;
     q.hdr = (int *)ws;
@@ -797,7 +861,7 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     io.state = (double *)((char *)ws + WS_HEADER + (size_t)q.cap * sizeof(int));
     io.quantum = env_int("SCPB200_QUANTUM", 1);
     io.snap = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
-    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d));
+    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d, rate));
     k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, order, env_int("SCPB200_PINNED", pl.grid / 2),
                                                       p->qp_warm_start && p->qp_warm_carry, q, io.state);
     CUDA_TRY(cudaGetLastError());
@@ -805,6 +869,7 @@ extern "C" int scpb200_scp_solve_ordered(const scpb200_dims *d, const scpb200_pa
     ka.d = *d; ka.p = *p; ka.io = io; ka.q = q; ka.gws = gws; ka.gl_stride = pl.gl_stride; ka.sh_lim = pl.sh_lim;
     ka.alpha_slots = pl.alpha_slots; ka.want_H = pl.want_H;
     memset(&ka.ro, 0, sizeof ka.ro);
+    if (entry_ensure(pl.entry, pl.threads, pl.smem_bytes)) return set_err(SCPB200_ERR_CUDA, "k_scp_solve cannot be resident");
     if (pl.entry->launch(pl.grid, pl.threads, pl.smem_bytes, stream, &ka)) {
         cudaGetLastError();
         return set_err(SCPB200_ERR_CUDA, "k_scp_solve launch failed");
@@ -827,8 +892,12 @@ extern "C" int scpb200_mpc_rollout(const scpb200_dims *d, const scpb200_params *
     if (d->nObst && (!r->dsafe_obst || !r->obst)) return set_err(SCPB200_ERR_ARG, "obstacle arrays required when nObst > 0");
     if (p->max_scp_iter < 1) return set_err(SCPB200_ERR_ARG, "max_scp_iter must be >= 1");
     if (d->B == 0) return 0;
+    const int rate = p->enable_rate_rows != 0;
+    if (rate && !(p->duLim > 0.0)) return set_err(SCPB200_ERR_ARG, "enable_rate_rows needs duLim > 0");
     SolvePlan pl;
+    g_plan_rate_rows = rate;
     rc = plan_scp(d, &pl);
+    g_plan_rate_rows = 0;
     if (rc) return rc;
     ScpIO io = {r->g, r->cterm, r->H, r->qv, r->gamma0, r->dsafe, r->dsafe_obst, r->obst, r->u, r->traj, r->U, (double *)0, r->obj,
                 r->max_violation, r->scp_iters, r->ipm_iters, r->status};
@@ -841,7 +910,8 @@ extern "C" int scpb200_mpc_rollout(const scpb200_dims *d, const scpb200_params *
     io.quantum = env_int("SCPB200_QUANTUM", 1);
     io.snap = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B));
     io.coherent = 1;
-    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d));
+    io.u_prev = r->u0;                                        // the set-up input of the step = the command being actuated
+    double *gws = (double *)((char *)ws + WS_HEADER + queue_bytes(d->B) + snap_bytes(d, rate));
     k_queue_init<<<(q.cap + 255) / 256, 256, 0, st>>>(d->B, (const int32_t *)0, 0, 0, q, io.state);
     CUDA_TRY(cudaGetLastError());
     ScpKernelArgs ka;
@@ -864,7 +934,8 @@ extern "C" int scpb200_mpc_rollout(const scpb200_dims *d, const scpb200_params *
     else if (pl.entry->max_threads > 256) re = pl.all_shared ? scp_entry_ro_generic_shared_wide() : scp_entry_ro_generic_global_wide();
     else re = pl.all_shared ? scp_entry_ro_generic_shared() : scp_entry_ro_generic_global();
     int occ = 0;
-    if (re->prepare(pl.threads, pl.smem_bytes, &occ) || occ < 1) return set_err(SCPB200_ERR_CUDA, "rollout kernel cannot be resident");
+    (void)occ;
+    if (entry_ensure(re, pl.threads, pl.smem_bytes)) return set_err(SCPB200_ERR_CUDA, "rollout kernel cannot be resident");
     if (re->launch(pl.grid, pl.threads, pl.smem_bytes, stream, &ka)) {
         cudaGetLastError();
         return set_err(SCPB200_ERR_CUDA, "k_scp_solve (rollout) launch failed");

@@ -111,24 +111,44 @@ extern "C" int emu_qp_solve_dense(const scpb200_dims *d, const scpb200_params *p
     return 0;
 }
 
+extern "C" int emu_scp_solve_rate(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                                  const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                                  const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                                  double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                                  double *max_violation, const double *u_prev);
+
 extern "C" int emu_scp_solve(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
                              const double *H, const double *qv, const double *gamma0, const double *dsafe,
                              const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
                              double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
                              double *max_violation)
 {
+    return emu_scp_solve_rate(d, p, g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, scp_iters, ipm_iters,
+                              status, obj, max_violation, (const double *)0);
+}
+
+// as scpb200_scp_solve_rate: with p->enable_rate_rows the steering-rate rows anchored at u_prev[B][nVeh]
+extern "C" int emu_scp_solve_rate(const scpb200_dims *d, const scpb200_params *p, const double *g, const double *cterm,
+                                  const double *H, const double *qv, const double *gamma0, const double *dsafe,
+                                  const double *dsafe_obst, const double *obst, double *u_inout, double *traj, double *U,
+                                  double *log, int32_t *scp_iters, int32_t *ipm_iters, int32_t *status, double *obj,
+                                  double *max_violation, const double *u_prev)
+{
+    const int rate = p->enable_rate_rows != 0;
+    if (rate && !u_prev) return -1;
     Cta *cta = new_cta();
     const int slots = g_alpha_slots < 0 ? g_nt / 32 : g_alpha_slots;
     size_t shu, glu;
     const size_t lim = g_force_global_S ? 3000 : ((size_t)1 << 40);
-    scp_footprint(d->nVeh, d->Hp, d->nObst, slots, 1, lim, &shu, &glu);
+    scp_footprint(d->nVeh, d->Hp, d->nObst, slots, 1, lim, &shu, &glu, SCP_RED_DOUBLES, rate);
     std::vector<double> smem(shu + 2), gmem(glu + 2);
     ScpBump bp = scp_bump(smem.data(), lim, gmem.data(), false);
     ScpMem s;
-    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1);
+    scp_carve(bp, s, d->nVeh, d->Hp, d->nObst, slots, 1, SCP_RED_DOUBLES, rate);
     ScpIO io = {g, cterm, H, qv, gamma0, dsafe, dsafe_obst, obst, u_inout, traj, U, log, obj, max_violation,
                 scp_iters, ipm_iters, status};
-    const size_t snapw = ipm_snap_doubles(s.ipm.n1p, s.ipm.mc);
+    io.u_prev = u_prev;
+    const size_t snapw = ipm_snap_doubles(s.ipm.n1p, s.ipm.mc, s.ipm.nr);
     std::vector<double> snapbuf((size_t)d->B * snapw, 0.0);
     io.snap = snapbuf.data();
     // SCPB200_EMU_QUANTUM=q: exercise the park / resume path of the work-queue scheduler (q SCP iterations per

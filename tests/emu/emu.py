@@ -114,7 +114,7 @@ def qp_solve_dense(P, q, A, b, lb, ub, params):
     return dict(x=x, fval=fval, iters=iters, status=status, zA=zA)
 
 
-def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=None):
+def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=None, u_prev=None):
     g, cterm, H, qv, gamma0, dsafe = _c(g), _c(cterm), _c(H), _c(qv), _c(gamma0), _c(dsafe)
     B, nVeh, Hp = g.shape[0], g.shape[1], g.shape[2]
     nObst, dso, ob = _obst(dsafe_obst, obst)
@@ -125,8 +125,10 @@ def scp_solve(g, cterm, H, qv, gamma0, dsafe, u, params, dsafe_obst=None, obst=N
     log = np.zeros((B, params.max_scp_iter, capi.LOG_W))
     si, ii, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
     obj, mv = np.zeros(B), np.zeros(B)
-    lib().emu_scp_solve(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(gamma0), _d(dsafe), _d(dso), _d(ob),
-                        _d(u), _d(traj), _d(U), _d(log), _i(si), _i(ii), _i(st), _d(obj), _d(mv))
+    up = None if u_prev is None else _c(u_prev).reshape(B, nVeh)
+    rc = lib().emu_scp_solve_rate(C.byref(d), C.byref(params), _d(g), _d(cterm), _d(H), _d(qv), _d(gamma0), _d(dsafe), _d(dso),
+                                  _d(ob), _d(u), _d(traj), _d(U), _d(log), _i(si), _i(ii), _i(st), _d(obj), _d(mv), _d(up))
+    assert rc == 0, "emu_scp_solve_rate: enable_rate_rows needs u_prev"
     return dict(u=u, traj=traj, U=U, log=log, scp_iters=si, ipm_iters=ii, status=st, obj=obj, max_violation=mv)
 
 

@@ -258,6 +258,100 @@ def test_trust_region_vs_oracle(mods, oracle, fname):
     assert 1 <= int(host(bs.scp_iters)[0]) <= 100 and (host(bs.status)[0] & (mods["capi"].ST_QP_MAXITER | mods["capi"].ST_QP_PIVOT)) == 0
 
 
+RATE_CASES = [f for f in ("circle8_hp10_step10.npz", "circle8_hp10_step29.npz", "circle3_hp10_step8.npz", "circle8_hp20_step7.npz")
+              if f in ALL_STEP_FILES]
+
+
+@pytest.mark.parametrize("fname", RATE_CASES)
+def test_rate_rows_vs_oracle(mods, oracle, fname):
+    """Steering-rate rows inside the QP (scpb200_params.enable_rate_rows, north-star item 2; the reference only clamps after
+    the solve, main.py:164-174).  K4 carries them as a tridiagonal term of the vehicle blocks; the oracle solves the same QPs
+    with the rows as dense rows.  Teacher-forced, bound chosen so that the rows bind: u within 1e-6, objective within 1e-6
+    relative, every steering step within the bound; then the free-running loop against the oracle's."""
+    G = load_golden(fname)
+    x0, u0, veh, poly = golden_setup_inputs(G)
+    nVeh, Hp = int(G["sc_nVeh"]), int(G["sc_Hp"])
+    S = oracle.mpc_setup(x0, u0, veh, poly, Hp=Hp, dt=float(G["sc_dt"]))
+    u_prev = np.asarray(u0, dtype=float).reshape(-1)[:nVeh]
+    O0, _ = _oracle_teacher(oracle, G, S, max_scp_iter=1)
+    steps0 = np.abs(np.diff(np.concatenate([u_prev[:, None], O0["u_hist"][0].reshape(nVeh, Hp)], axis=1), axis=1))
+    du = 0.5 * steps0.max()
+    assert du > 1e-5
+    O, ubars = _oracle_teacher(oracle, G, S, max_scp_iter=8, u_prev=u_prev, duLim=du)
+    nit = len(ubars)
+    bs = make_batch(mods, G, B=nit, max_scp_iter=1, enable_rate_rows=1, duLim=du)
+    bs.load_inputs(u=ubars)
+    bs.controller_step()
+    u, log, st = host(bs.u), host(bs.log), host(bs.status)
+    assert (st & (mods["capi"].ST_QP_MAXITER | mods["capi"].ST_QP_PIVOT) == 0).all()
+    assert np.abs(u - O["u_hist"]).max() < 1e-6
+    steps = np.abs(np.diff(np.concatenate([np.repeat(u_prev[None, :, None], nit, axis=0), u.reshape(nit, nVeh, Hp)], axis=2), axis=2))
+    assert steps.max() <= du + 1e-8 and steps.max() > du - 1e-7
+    assert np.abs(log[:, 0, 1] - O["log"][:, 1]).max() <= 1e-6 * np.abs(O["log"][:, 1]).max()
+    print(f"\n[rate rows {fname}] {nit} QPs, du = {du:.3e}: max |u-u*| {np.abs(u - O['u_hist']).max():.2e}, "
+          f"largest steering step {steps.max():.6e}")
+    # free-running with the reference's own bound (6 deg per step: inactive next to |u| <= 3 deg, so the run equals the
+    # run without the rows) and with the binding bound against the oracle
+    tight = dict(abstol=1e-10, reltol=1e-10, feastol=1e-9)
+    Of = oracle.scp_optimizer(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], float(S["gamma0"][0]), G["sc_dsafeVehicles"], G["u_warm"],
+                              dsafeExtra=float(G["sc_dsafeExtra"]), uLim=float(G["sc_uLim"]), opts=tight, u_prev=u_prev, duLim=du)
+    bs = make_batch(mods, G, B=1, enable_rate_rows=1, duLim=du)
+    bs.load_inputs(u=np.asarray(G["u_warm"], dtype=float)[None])
+    bs.controller_step()
+    if Of["iters"] <= 6:
+        assert int(host(bs.scp_iters)[0]) == Of["iters"]
+        assert np.abs(host(bs.u)[0] - Of["u"]).max() < 1e-6
+    ref_du = float(G["sc_duLim"])
+    a = make_batch(mods, G, B=1)
+    a.load_inputs(u=np.asarray(G["u_warm"], dtype=float)[None]); a.controller_step()
+    b = make_batch(mods, G, B=1, enable_rate_rows=1, duLim=ref_du)
+    b.load_inputs(u=np.asarray(G["u_warm"], dtype=float)[None]); b.controller_step()
+    assert int(host(a.scp_iters)[0]) == int(host(b.scp_iters)[0])
+    assert np.abs(host(a.u) - host(b.u)).max() < 1e-6
+
+
+def test_rate_rows_contract_and_rollout(mods):
+    """enable_rate_rows without u_prev is an argument error of the plain entries (not a silent fall-back); the rollout entry
+    (u_prev = the set-up input u0 of each step) equals the per-step call sequence bit for bit; every applied steering step
+    of the closed loop respects the bound without the post-solve clamp having to act."""
+    torch, capi, batch, scen = mods["torch"], mods["capi"], mods["batch"], mods["scen"]
+    B, nVeh, Hp, nsteps = 24, 8, 10, 4
+    du = 0.15 * scen.DU_LIM
+    cb = scen.circle_batch(B, nVeh=nVeh, Hp=Hp, instance0=0, step_lo=4, step_hi=7)
+
+    def fresh():
+        p = capi.Params()
+        capi.load().scpb200_default_params(C.byref(p))
+        p.enable_rate_rows, p.duLim = 1, du
+        bs = batch.BatchSCP(B, nVeh, Hp, params=p)
+        bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, nVeh * Hp)))
+        return bs
+
+    bs = fresh()
+    bs.setup()
+    rc = bs.lib.scpb200_scp_solve(C.byref(bs.dims), C.byref(bs.params), *[C.c_void_p(t.data_ptr()) for t in (bs.g, bs.cterm, bs.H, bs.qv, bs.gamma0, bs.dsafe)],
+                                  None, None, C.c_void_p(bs.u.data_ptr()), C.c_void_p(bs.traj.data_ptr()), C.c_void_p(bs.U.data_ptr()), None,
+                                  *[C.c_void_p(t.data_ptr()) for t in (bs.scp_iters, bs.ipm_iters, bs.status, bs.obj, bs.max_violation, bs.ws)], None)
+    assert rc == -1 and b"u_prev" in bs.lib.scpb200_last_error()
+    a = fresh()
+    worst = 0.0
+    for s in range(nsteps):
+        a.params.noise_counter = s
+        u_before = a.u0.clone()
+        a.setup(); a.solve()
+        worst = max(worst, float((a.U[:, 0, :] - u_before).abs().max()))
+        a.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+    assert worst <= du + 1e-8, worst
+    assert worst > 0.5 * du                                                # the bound matters on this workload
+    r = fresh()
+    r.params.noise_counter = 0
+    r.rollout(nsteps, scen.MECH_LIMIT, scen.DU_LIM)
+    torch.cuda.synchronize()
+    for k in ("u", "U", "x0", "u0", "scp_iters", "ipm_iters", "status"):
+        assert torch.equal(getattr(a, k), getattr(r, k)), k
+    print(f"\n[rate rows closed loop] {B} instances x {nsteps} steps: largest applied steering step {worst:.6e} (bound {du:.6e})")
+
+
 def test_obstacle_rows_vs_oracle(mods, oracle):
     """Obstacle rows (SCP_controller.py:106-114, 321-326) in K4, K2 and the evaluate kernel against the
     oracle with the same two static obstacles."""

@@ -319,6 +319,64 @@ def test_trust_region_rows_vs_oracle(oracle):
     assert np.abs(r["u"] - ubars).max() > 0.99 * rho                      # the trust region binds on this step
 
 
+@pytest.mark.parametrize("fname,nt", [("circle8_hp10_step29.npz", 128), ("circle8_hp10_step10.npz", 256), ("circle3_hp10_step8.npz", 128)])
+def test_rate_rows_vs_oracle(oracle, fname, nt):
+    """The steering-rate rows of scpb200_params.enable_rate_rows (north-star item 2; the reference only clamps after the
+    solve, main.py:164-174): |u_v[k] - u_v[k-1]| <= duLim with u_v[-1] = the command being actuated, as a tridiagonal term
+    of the normal matrix.  Teacher-forced against the oracle's run with the same rows as dense rows; the bound is chosen so
+    that it binds."""
+    if fname not in ALL_STEP_FILES:
+        pytest.skip("fixture not present")
+    emu.config(nt=nt, reverse=False)
+    G = load_golden(fname)
+    S = _setup(oracle, G)
+    nVeh, Hp = S["g"].shape[1], S["g"].shape[2]
+    u_prev = np.array(G["u0"], dtype=float).reshape(-1)[:nVeh]
+    # unconstrained (in rate) solution of the first QP: how fast does it steer?
+    O0, ub0 = _oracle_teacher(oracle, G, S, max_scp_iter=1)
+    steps0 = np.abs(np.diff(np.concatenate([u_prev[:, None], O0["u_hist"][0].reshape(nVeh, Hp)], axis=1), axis=1))
+    du = 0.5 * steps0.max()
+    assert du > 1e-5
+    O, ubars = _oracle_teacher(oracle, G, S, max_scp_iter=8, u_prev=u_prev, duLim=du)
+    nit = len(ubars)
+    rep = lambda a: np.repeat(a, nit, axis=0)
+    r = emu.scp_solve(rep(S["g"]), rep(S["cterm"]), rep(S["H"]), rep(S["qv"]), rep(S["gamma0"]), rep(G["sc_dsafeVehicles"][None]),
+                      ubars, params_for(G, max_scp_iter=1, enable_rate_rows=1, duLim=du), u_prev=rep(u_prev[None]))
+    assert (r["status"] & 3 == 0).all()
+    assert np.abs(r["u"] - O["u_hist"]).max() < 1e-6
+    steps = np.abs(np.diff(np.concatenate([rep(u_prev[None])[:, :, None], r["u"].reshape(nit, nVeh, Hp)], axis=2), axis=2))
+    assert steps.max() <= du + 1e-8
+    assert steps.max() > du - 1e-7                                         # the rows bind
+    assert np.abs(r["log"][:, 0, 1] - O["log"][:, 1]).max() <= 1e-6 * np.abs(O["log"][:, 1]).max()
+    # rows off (the default): the result is that of the reference's QP, bit for bit the same as without the field
+    a = emu.scp_solve(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], ubars[:1], params_for(G, max_scp_iter=1))
+    b = emu.scp_solve(S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], ubars[:1],
+                      params_for(G, max_scp_iter=1, enable_rate_rows=0, duLim=du), u_prev=u_prev[None])
+    assert np.array_equal(a["u"], b["u"])
+
+
+def test_rate_rows_free_running_and_parked(oracle, monkeypatch):
+    """Free-running SCP loop with rate rows: same iteration count and result as the oracle on a stable step, and the park /
+    resume path (warm-start snapshot with the rate rows' slacks and multipliers) is bit-identical to the uninterrupted loop."""
+    G = load_golden("circle8_hp10_step10.npz")
+    S = _setup(oracle, G)
+    nVeh, Hp = S["g"].shape[1], S["g"].shape[2]
+    u_prev = np.array(G["u0"], dtype=float).reshape(-1)[:nVeh]
+    du = float(G["sc_duLim"]) if "sc_duLim" in G else np.pi / 180 * 6
+    tight = dict(abstol=1e-10, reltol=1e-10, feastol=1e-9)
+    O = oracle.scp_optimizer(S["g"][0], S["cterm"][0], S["H"][0], S["qv"][0], float(S["gamma0"][0]), G["sc_dsafeVehicles"], G["u_warm"],
+                             dsafeExtra=float(G["sc_dsafeExtra"]), uLim=float(G["sc_uLim"]), opts=tight, u_prev=u_prev, duLim=du)
+    args = (S["g"], S["cterm"], S["H"], S["qv"], S["gamma0"], G["sc_dsafeVehicles"][None], np.array(G["u_warm"], dtype=float).reshape(1, -1))
+    P = params_for(G, enable_rate_rows=1, duLim=du)
+    r = emu.scp_solve(*args, P, u_prev=u_prev[None])
+    assert int(r["scp_iters"][0]) == O["iters"]
+    assert np.abs(r["u"][0] - O["u"]).max() < 1e-6
+    monkeypatch.setenv("SCPB200_EMU_QUANTUM", "1")
+    monkeypatch.setenv("SCPB200_EMU_POISON", "1")
+    q = emu.scp_solve(*args, P, u_prev=u_prev[None])
+    assert np.array_equal(q["u"], r["u"]) and int(q["ipm_iters"][0]) == int(r["ipm_iters"][0])
+
+
 def test_obstacle_rows_vs_oracle(oracle):
     """Obstacle rows (SCP_controller.py:106-114, 321-326): two static obstacles next to the paths of the
     3-vehicle scenario, teacher-forced against the oracle's own run with the same obstacles."""
