@@ -338,6 +338,11 @@ SCP_FN void chol_factor(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
 //   * plain tile-wise substitution by one warp, diagonal tile solved by one lane: 14 k cycles per triangular solve;
 //   * 32 x 32 diagonal blocks inverted, block substitution with lane = row: 15 k (the per-lane row-dots serialise on
 //     shared-memory latency: the compiler keeps one load in flight).
+//   * the whole substitution inside ONE warp with the vector in registers (row i = lane + 32 m), the 8 unknowns of a tile
+//     column gathered and broadcast by shuffles, no barrier (round 2): ~260 instructions per tile column, which a lone
+//     warp issues at ~5 cycles each (every instruction waits on the one before: shuffle 25, LDS 30, DFMA 9) = 1.3 k cycles per
+//     column against 715 for the version below; the step fell from 603 k to 433 k QP/s (ncu: 25 % of the warp samples were the
+//     other three warps waiting for warp 0).  Not kept.
 // This version: only the 8 x 8 DIAGONAL TILES are inverted (in place, after the factorisation: one phase), and a
 // triangular solve is T steps inside warp 0 with no CTA barrier: 8 lanes apply the tile inverse (an 8 x 8 mat-vec), every
 // lane then takes the 8 new unknowns out of its rows below (forward) / columns to the left (backward).  All loads of a

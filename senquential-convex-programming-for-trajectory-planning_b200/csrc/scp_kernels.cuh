@@ -954,8 +954,10 @@ struct ScpIO {
 
 // SCP_optimizer (SCP_controller.py:74-197) + the result shaping of SCP_controller (:68-70) for instance b.
 // Returns true when the instance is finished (results written), false when it was parked.
+// pin: -1 = the instance's own flag (state[5], set when the queue is filled); 0 / 1 = the caller's decision for this
+// invocation (the rollout entry pins the instances that are furthest behind).  Must be uniform over the CTA.
 SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_params &p, int b, const ScpIO &io,
-                               ScpMem &s)
+                               ScpMem &s, int pin = -1)
 {
     const int nVeh = d.nVeh, Hp = d.Hp, nObst = d.nObst, n = nVeh * Hp;
     const int mcv = Hp * (nVeh * (nVeh - 1) / 2), mc = mcv + Hp * nVeh * nObst;
@@ -1025,7 +1027,8 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         snap_valid = (int)SCP_LD_COHERENT(stB + 6);
         ev.obj = obj0; ev.max_violation = mv0; ev.sum_violations = 0.0; ev.feasible = mv0 > 0.0 ? 0 : 1;
     }
-    const int it_park = (stB && stB[5] == 0.0) ? it + (io.quantum > 0 ? io.quantum : 1) : p.max_scp_iter;
+    const bool parks = stB && (pin < 0 ? stB[5] == 0.0 : pin == 0);
+    const int it_park = parks ? it + (io.quantum > 0 ? io.quantum : 1) : p.max_scp_iter;
     for (; it < p.max_scp_iter; ++it) {
         if (it >= it_park) {
             // park: u and the loop scalars go back to global memory; another invocation continues from here

@@ -22,6 +22,10 @@
 //   hdr[0] = head ticket, hdr[1] = tail ticket, hdr[2] = instances not yet finished; slots[cap], cap = power of two
 //   >= 2B, empty = -1.  Pop ticket h is served by push ticket h (FIFO); a popper whose ticket is never served leaves
 //   when hdr[2] reaches 0.
+// Rollout entry only: hdr[3] = the lowest MPC step any instance is still at, hdr[SCP_Q_CNT + s] = instances at step s
+// (s < SCP_Q_STEPS; longer rollouts run without the laggard rule below).
+#define SCP_Q_CNT 64
+#define SCP_Q_STEPS 4096
 struct WorkQueue {
     int *hdr, *slots;
     int cap;
@@ -78,7 +82,7 @@ __device__ __forceinline__ int queue_pop(const WorkQueue &q)
 // has run all its MPC steps.  k1ws / k1_warps: shared scratch for the warp-level set-up (the normal-matrix area, dead
 // between QPs).
 __device__ __forceinline__ bool rollout_invocation(Cta &cta, const scpb200_dims &d, const ScpKernelArgs &a, int b, ScpMem &s,
-                                                   double *k1ws, int k1_warps, int *setup_flag)
+                                                   double *k1ws, int k1_warps, int *setup_flag, int pin)
 {
     double *stB = a.io.state + (size_t)b * SCP_STATE_W;
     const int it_resume = (int)SCP_LD_COHERENT(stB + 2), step = (int)SCP_LD_COHERENT(stB + 7);
@@ -86,10 +90,20 @@ __device__ __forceinline__ bool rollout_invocation(Cta &cta, const scpb200_dims 
         scp_rollout_setup(cta, d, a.p, a.ro, b, step, s.resp, s.ipm.red, setup_flag, k1ws, k1_warps);
         __syncthreads();
     }
-    if (!scp_solve_instance(cta, d, a.p, b, a.io, s)) return false;
+    if (!scp_solve_instance(cta, d, a.p, b, a.io, s, pin)) return false;
     __syncthreads();
     scp_rollout_advance(cta, d, a.p, a.ro, a.io, b, step);
     if (threadIdx.x == 0) {
+        if (a.ro.nsteps <= SCP_Q_STEPS) {
+            // the instance moves from step to step + 1 (added before it is removed: the counts never undercount), and the
+            // lowest live step moves up past every step nobody is at any more
+            int *cnt = a.q.hdr + SCP_Q_CNT;
+            if (step + 1 < a.ro.nsteps) atomicAdd(cnt + step + 1, 1);
+            atomicSub(cnt + step, 1);
+            int m = *(volatile int *)(a.q.hdr + 3);
+            while (m < a.ro.nsteps - 1 && *(volatile int *)(cnt + m) == 0) ++m;
+            atomicMax(a.q.hdr + 3, m);
+        }
         stB[7] = (double)(step + 1);
         stB[2] = 0.0;                                          // the next invocation starts a fresh SCP loop ...
         if (!(a.p.qp_warm_start && a.p.qp_warm_carry)) stB[6] = 0.0;   // ... cold, as a new scpb200_scp_solve call would
@@ -112,6 +126,8 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
     extern __shared__ double sh[];
     __shared__ int slot;
     __shared__ int setup_flag;
+    __shared__ int pin_flag;
+    int carry = -1;                                // thread 0: the instance this CTA keeps instead of re-queueing it
     scpb200_dims d = a.d;
     if (NVEH > 0) { d.nVeh = NVEH; d.Hp = HP; d.nObst = 0; }
     const int alpha_slots = NVEH > 0 ? SCP_FIXED_ALPHA : a.alpha_slots, want_H = (NVEH > 0 && HP <= 10) ? 0 : a.want_H;
@@ -123,9 +139,25 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
     scp_carve(bp, s, d.nVeh, d.Hp, d.nObst, alpha_slots, want_H, SCP_RED_DOUBLES, rate_rows);
     for (;;) {
         if (threadIdx.x == 0) {
-            const int b = queue_pop(a.q);
+            const int b = carry >= 0 ? carry : queue_pop(a.q);
+            carry = -1;
             __threadfence();                       // acquire: the parked state written by the CTA that pushed b
             slot = b;
+            if (ROLLOUT) {
+                // Laggard rule.  Across MPC steps the batch ends on the instance with the most QPs IN TOTAL, and a FIFO ring
+                // advances every live instance by one QP per round: the heavy instances fall behind in steps and run
+                // alone at the end (measured: the rollout was slower than the per-step calls it replaces).  An instance
+                // that is at the lowest live step is therefore never parked and never re-queued: its chain of QPs runs
+                // without waiting, everything else fills the other CTAs round-robin.  In the last step every instance is
+                // a laggard and the QP-granular round-robin of the per-step kernel applies again.  Scheduling only:
+                // results do not depend on it (park / resume is bit-identical).
+                int pin = 0;
+                if (b >= 0 && a.ro.nsteps <= SCP_Q_STEPS) {
+                    const int step = (int)SCP_LD_COHERENT(a.io.state + (size_t)b * SCP_STATE_W + 7);
+                    pin = step <= *(volatile int *)(a.q.hdr + 3) && step < a.ro.nsteps - 1;
+                }
+                pin_flag = pin;
+            }
         }
         __syncthreads();
         const int b = slot;
@@ -136,7 +168,7 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
             const int ntile = s.ipm.T * (s.ipm.T + 1) / 2;
             double *k1ws = ALL_SHARED ? s.ipm.S : s.ipm.bA;
             const int k1_doubles = ALL_SHARED ? ntile * SCP_TILE2 : 8 * s.ipm.mc;
-            done = rollout_invocation(cta, d, a, b, s, k1ws, scp_imax(1, k1_doubles / SCP_K1_WARP_DOUBLES), &setup_flag);
+            done = rollout_invocation(cta, d, a, b, s, k1ws, scp_imax(1, k1_doubles / SCP_K1_WARP_DOUBLES), &setup_flag, pin_flag);
         } else {
             (void)setup_flag;
             done = scp_solve_instance(cta, d, a.p, b, a.io, s);
@@ -145,6 +177,9 @@ k_scp_solve(const __grid_constant__ ScpKernelArgs a)
         __syncthreads();                           // ... are ordered before thread 0 hands the instance on
         if (threadIdx.x == 0) {
             if (done) atomicSub(a.q.hdr + 2, 1);
+            else if (ROLLOUT && a.ro.nsteps <= SCP_Q_STEPS &&
+                     (int)a.io.state[(size_t)b * SCP_STATE_W + 7] <= *(volatile int *)(a.q.hdr + 3) &&
+                     (int)a.io.state[(size_t)b * SCP_STATE_W + 7] < a.ro.nsteps - 1) carry = b;   // still furthest behind: keep it
             else queue_push(a.q, b);
         }
     }

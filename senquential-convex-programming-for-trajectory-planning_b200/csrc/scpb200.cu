@@ -252,6 +252,7 @@ __device__ __forceinline__ int next_instance(int *counter, int *slot)
 __global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_snap, WorkQueue q, double *state)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = i; s < SCP_Q_STEPS; s += gridDim.x * blockDim.x) q.hdr[SCP_Q_CNT + s] = s == 0 ? B : 0;   // rollout: everyone at step 0
     if (i < q.cap) q.slots[i] = i < B ? (order ? order[i] : i) : -1;
     if (i < B) {
         const int b = order ? order[i] : i;
@@ -260,7 +261,7 @@ __global__ void k_queue_init(int B, const int32_t *order, int npinned, int keep_
         state[(size_t)b * SCP_STATE_W + 7] = 0.0;                  // rollout entry: MPC step the instance is at
         if (!keep_snap) state[(size_t)b * SCP_STATE_W + 6] = 0.0;    // no warm-start iterate from an earlier call
     }
-    if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; }
+    if (i == 0) { q.hdr[0] = 0; q.hdr[1] = B; q.hdr[2] = B; q.hdr[3] = 0; }
 }
 
 // Pull order for the work queue: instances sorted by DEscending expected work (longest-processing-time-first), so
@@ -324,7 +325,7 @@ struct SolvePlan {
     const ScpKernelEntry *entry;             // K4: the instantiation this plan launches
 };
 
-#define WS_HEADER 256
+#define WS_HEADER (256 + 4 * SCP_Q_STEPS)   /* queue header (64 ints) + the rollout entry's per-step instance counts */
 static size_t queue_cap(long B)
 {
     size_t c = 64;
@@ -784,7 +785,7 @@ extern "C" int scpb200_qp_solve_dense(const scpb200_dims *d, const scpb200_param
     if (rc) return rc;
     QpIO io = {P, q, A, b, lb, ub, x, fval, zA, iters, status};
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaMemsetAsync(ws, 0, WS_HEADER, st));
+    CUDA_TRY(cudaMemsetAsync(ws, 0, 256, st));
     int *counter = (int *)ws;
     double *gws = (double *)((char *)ws + WS_HEADER);
     if (pl.all_shared)
