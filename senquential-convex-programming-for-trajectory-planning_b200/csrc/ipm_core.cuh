@@ -255,6 +255,12 @@ SCP_FN void warp_tile_syrk2(int lane, double *C, const double *A, const double *
 }
 
 // ------------------------------------------------------------------------------------------------ Cholesky
+// (Round 2, long horizons with the matrix in the L2-resident workspace: FOUR trailing tiles in flight per warp instead of
+// two made the update 3 x slower, 3.3 M against 1.06 M cycles per factorisation at Hp = 50.  The update is not bound by
+// the latency of a round trip: it moves 1.8 KB per tile product through the SM's 64 B / cycle path to L2, >= 620 k cycles
+// per factorisation, and the paired order keeps the panel tiles in L1 where the strided order of four does not.  What
+// helps there is less traffic — accumulators in registers over the tile columns, the shared operand row staged in shared
+// memory — not more loads in flight.  profiles/r02_hp50_four_tiles_in_flight_and_prefetch_experiment_phase_timers.txt)
 // In-place blocked right-looking Cholesky of the tile-packed lower triangle: on exit m.S holds L, m.dinv the
 // reciprocal pivots.
 //   per tile column K:  (a) lane 0 factors the diagonal tile (in the shadow of the previous trailing update),
@@ -343,6 +349,13 @@ SCP_FN void chol_factor(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
 //     warp issues at ~5 cycles each (every instruction waits on the one before: shuffle 25, LDS 30, DFMA 9) = 1.3 k cycles per
 //     column against 715 for the version below; the step fell from 603 k to 433 k QP/s (ncu: 25 % of the warp samples were the
 //     other three warps waiting for warp 0).  Not kept.
+//   * one CTA barrier per BLOCK of four tile columns instead of one per column (round 2; warp 0 solves the block with
+//     warp-level synchronisation only, the other warps take the previous block's 32 unknowns out of everything beyond it):
+//     25.1 k cycles per iteration against 23.6 k, 578 k QP/s against 590-603 k.  The barrier is not what a column costs: it
+//     is the three dependent shared-memory round trips inside warp 0 (row-dot -> store -> row-dot), which blocking keeps.
+//     Not kept.
+//   * long horizons (factor in the L2-resident workspace, Hp = 50): the next step's rows / columns fetched into registers
+//     before the barrier that ends a step (round 2): 517 k cycles per iteration with and without.  Not kept.
 // This version: only the 8 x 8 DIAGONAL TILES are inverted (in place, after the factorisation: one phase), and a
 // triangular solve is T steps inside warp 0 with no CTA barrier: 8 lanes apply the tile inverse (an 8 x 8 mat-vec), every
 // lane then takes the 8 new unknowns out of its rows below (forward) / columns to the left (backward).  All loads of a
