@@ -502,7 +502,9 @@ def run_product(args):
         setup_roof = {"bound": "hbm", "kernel": "k_mpc_setup", "achieved": k1_ach, "peak": peaks_["hbm_gbs"], "unit": "GB/s",
                       "frac": k1_ach / peaks_["hbm_gbs"], "ms_per_launch": float(setup_ms.mean()), "algorithmic_bytes_per_launch": k1_bytes,
                       "share_of_step": float(setup_ms.sum() / step_ms.sum()), "peak_source": how_,
-                      "note": "latency-bound at this batch (one warp per vehicle, 8x8 Pade products on DMMA); bytes = inputs + every K1 output"}
+                      "note": "instruction-bound, not memory-bound (ncu, profiles/r02_end_k_mpc_setup_details.txt: IPC 2.07, issue slots 52 % busy, DRAM "
+                              "throughput 0.1 %): one warp per vehicle, 8x8 Pade products on DMMA, reference sampler and Toeplitz recurrences by "
+                              "lanes; bytes = inputs + every K1 output"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
