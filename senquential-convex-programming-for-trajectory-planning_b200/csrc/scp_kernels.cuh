@@ -1066,15 +1066,21 @@ SCP_FN bool scp_solve_instance(Cta &cta, const scpb200_dims &d, const scpb200_pa
         IpmResult res;
         int warm_iters = 0;                                 // iterations of an abandoned warm attempt (logged with the QP)
         ctl.warm = ctl.snap && snap_valid;
-        if (ctl.warm) {
-            // a warm start that does not converge quickly (the active set moved too far) is abandoned for a cold one
+        {
+            // ONE call site of the solver for the warm attempt, its cold restart and the plain cold start: inlined three times
+            // the interior-point method was two thirds of the kernel's 390 KB of code, and the instruction cache of an SM
+            // that runs three CTAs in different phases missed on the critical lanes (ncu: stall_no_inst next to the
+            // shared-memory stalls in the substitution).
+            // A warm start that does not converge quickly (the active set moved too far) is abandoned for a cold one.
             const int cap = ctl.max_iter;
-            ctl.max_iter = p.qp_warm_max_iter > 0 ? p.qp_warm_max_iter : cap;
-            ipm_solve(cta, op, m, ctl, &res);
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                ctl.max_iter = (ctl.warm && p.qp_warm_max_iter > 0) ? p.qp_warm_max_iter : cap;
+                ipm_solve(cta, op, m, ctl, &res);
+                if (!(ctl.warm && (res.status & SCPB200_ST_QP_MAXITER))) break;
+                warm_iters = res.iters; ipm_total += res.iters; ctl.warm = 0;
+            }
             ctl.max_iter = cap;
-            if (res.status & SCPB200_ST_QP_MAXITER) { warm_iters = res.iters; ipm_total += res.iters; ctl.warm = 0; ipm_solve(cta, op, m, ctl, &res); }
-        } else {
-            ipm_solve(cta, op, m, ctl, &res);
         }
         // a warm-started QP that converged before it reached the iteration a new iterate is taken from leaves the old
         // one in place: it was a good start for this QP and the next one is closer still (SCP is converging)
