@@ -391,26 +391,25 @@ def run_product(args):
     ipm_per_step = ipm_counts.cpu().numpy()
 
     # ---------------- end-to-end through the public API with host buffers (e2e) ----------------
-    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).pin_memory()
-    h_in = {k: pin(getattr(cb, k)) for k in ("x0", "u0", "veh", "poly", "dsafe")}
-    h_in["u"] = pin(np.zeros((B, nVeh * Hp)))
-    h_out = {k: torch.empty_like(getattr(bs, k), device="cpu").pin_memory() for k in
-             ("U", "traj", "u", "scp_iters", "ipm_iters", "status", "obj", "max_violation", "x0", "u0")}
-    h2d = sum(t.numel() * t.element_size() for t in h_in.values())
-    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+    # The caller's state lives in host memory (a pinned HostIO mirror of the batch's I/O arena: x0, u0, veh, poly, dsafe, warm
+    # start u in; x0, u0, u, U, traj, obj, max_violation, iteration counts, status out).  Every step sends the inputs
+    # (one contiguous host -> device copy), runs the controller stage, reads every result back (one device -> host copy)
+    # and synchronises; the next step's x0 / u0 / u are the values just read back, in place in the host buffer.
+    hio = bs.host_io()
+    for k in ("x0", "u0", "veh", "poly", "dsafe"):
+        getattr(hio, k)[...] = np.asarray(getattr(cb, k)).reshape(getattr(hio, k).shape)
+    hio.u[...] = 0.0
+    h2d, d2h = hio.nbytes_in, hio.nbytes_out
 
     def e2e_step(s):
-        for k, t in h_in.items():                           # the caller's per-step inputs: measured state, scenario, warm start
-            getattr(bs, k).copy_(t, non_blocking=True)
+        bs.upload(hio)
         bs.params.noise_counter = s
         bs.setup()
         bs.solve()
         bs.advance_linear(uMax, duLim)
-        for k, t in h_out.items():
-            t.copy_(getattr(bs, k), non_blocking=True)
+        bs.download(hio)
         torch.cuda.synchronize(dev)
-        h_in["x0"].copy_(h_out["x0"]); h_in["u0"].copy_(h_out["u0"]); h_in["u"].copy_(h_out["u"])   # next step's host inputs
-        return int(h_out["scp_iters"].sum())
+        return int(hio.scp_iters.sum())
 
     for s in range(args.warmup):
         e2e_step(s)

@@ -57,13 +57,30 @@ class BatchSCP:
         i32 = dict(dtype=torch.int32, device=self.device)
         B_, V, Hp_ = self.B, self.nVeh, self.Hp
         with torch.cuda.device(self.device):
-            self.x0 = torch.zeros(B_, V, 6, **f64)
-            self.u0 = torch.zeros(B_, V, **f64)
-            self.veh = torch.zeros(B_, V, 5, **f64)
-            self.poly = torch.zeros(B_, V, self.nPts, 2, **f64)
-            self.dsafe = torch.zeros(B_, V, V, **f64)
-            self.dsafe_obst = torch.zeros(B_, V, self.nObst, **f64) if self.nObst else None
-            self.obst = torch.zeros(B_, self.nObst, Hp_, 2, **f64) if self.nObst else None
+            # The caller-facing inputs and results live in ONE contiguous device arena (self.io), every tensor a view of it:
+            # inputs only | in/out (x0, u0, u) | results.  A caller with HOST buffers (HostIO) then moves one contiguous range
+            # up and one down per MPC step instead of a copy per tensor.
+            spec = [("veh", (B_, V, 5), torch.float64), ("poly", (B_, V, self.nPts, 2), torch.float64),
+                    ("dsafe", (B_, V, V), torch.float64)]
+            if self.nObst:
+                spec += [("dsafe_obst", (B_, V, self.nObst), torch.float64), ("obst", (B_, self.nObst, Hp_, 2), torch.float64)]
+            spec += [("x0", (B_, V, 6), torch.float64), ("u0", (B_, V), torch.float64), ("u", (B_, self.n), torch.float64),
+                     ("U", (B_, Hp_, V), torch.float64), ("traj", (B_, Hp_, 2, V), torch.float64), ("obj", (B_,), torch.float64),
+                     ("max_violation", (B_,), torch.float64), ("scp_iters", (B_,), torch.int32),
+                     ("ipm_iters", (B_,), torch.int32), ("status", (B_,), torch.int32)]
+            self.io_layout, off = {}, 0
+            for name, shape, dt in spec:
+                nbytes = int(np.prod(shape)) * (8 if dt == torch.float64 else 4)
+                self.io_layout[name] = (off, nbytes, shape, dt)
+                off += (nbytes + 15) & ~15
+            self.io = torch.zeros(off, dtype=torch.uint8, device=self.device)
+            for name, (o, nbytes, shape, dt) in self.io_layout.items():
+                setattr(self, name, self.io[o:o + nbytes].view(dt).view(shape))
+            if not self.nObst:
+                self.dsafe_obst = self.obst = None
+            #: byte ranges of the arena a host caller sends per step (inputs + in/out) and reads back (in/out + results)
+            self.io_in_range = (0, self.io_layout["u"][0] + self.io_layout["u"][1])
+            self.io_out_range = (self.io_layout["x0"][0], off)
             self.ref = torch.zeros(B_, V, Hp_, 2, **f64)
             self.g = torch.zeros(B_, V, Hp_, 2, **f64)
             self.cterm = torch.zeros(B_, V, Hp_, 2, **f64)
@@ -72,16 +89,8 @@ class BatchSCP:
             self.gamma0 = torch.zeros(B_, **f64)
             self.abe = torch.zeros(B_, V, 48, **f64)
             self.setup_status = torch.zeros(B_, **i32)
-            self.u = torch.zeros(B_, self.n, **f64)
-            self.traj = torch.zeros(B_, Hp_, 2, V, **f64)
-            self.U = torch.zeros(B_, Hp_, V, **f64)
             self.log = None
             self._size_log()
-            self.scp_iters = torch.zeros(B_, **i32)
-            self.ipm_iters = torch.zeros(B_, **i32)
-            self.status = torch.zeros(B_, **i32)
-            self.obj = torch.zeros(B_, **f64)
-            self.max_violation = torch.zeros(B_, **f64)
             nbytes = C.c_size_t(0)
             check(self.lib.scpb200_workspace_bytes(C.byref(self.dims), C.byref(nbytes)), "scpb200_workspace_bytes")
             self.ws = torch.zeros(max(int(nbytes.value), 256), dtype=torch.uint8, device=self.device)
@@ -128,6 +137,20 @@ class BatchSCP:
             dst = getattr(self, name)
             src = torch.as_tensor(val, dtype=torch.float64)
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    def host_io(self) -> "HostIO":
+        """A pinned host mirror of the I/O arena (same layout, same tensor names as NumPy views)."""
+        return HostIO(self)
+
+    def upload(self, hio: "HostIO"):
+        """Host -> device: the step's inputs (veh, poly, dsafe[, obstacles], x0, u0, warm start u) in one copy."""
+        a, b = self.io_in_range
+        self.io[a:b].copy_(hio.buf[a:b], non_blocking=True)
+
+    def download(self, hio: "HostIO"):
+        """Device -> host: x0, u0, u and every result of the step in one copy (asynchronous: synchronise before reading)."""
+        a, b = self.io_out_range
+        hio.buf[a:b].copy_(self.io[a:b], non_blocking=True)
 
     # ------------------------------------------------------------------------------------------------ kernels
     def setup(self):
@@ -296,6 +319,21 @@ class BatchSCP:
                   "scpb200_ode_predict")
         self.kernel_launches += 1
         return out
+
+
+class HostIO:
+    """Pinned host staging buffer with the layout of BatchSCP.io; `h.x0`, `h.U`, ... are NumPy views of it.
+
+    The reference's caller keeps its state in host arrays (main.py:112-117); this is that state for B scenarios, laid
+    out so that BatchSCP.upload / download move it with one host<->device copy each."""
+
+    def __init__(self, bs: "BatchSCP"):
+        self.buf = torch.zeros(bs.io.numel(), dtype=torch.uint8).pin_memory()
+        self.nbytes_in = bs.io_in_range[1] - bs.io_in_range[0]
+        self.nbytes_out = bs.io_out_range[1] - bs.io_out_range[0]
+        raw = self.buf.numpy()
+        for name, (o, nbytes, shape, dt) in bs.io_layout.items():
+            setattr(self, name, raw[o:o + nbytes].view(np.float64 if dt == torch.float64 else np.int32).reshape(shape))
 
 
 def qp_solve_dense(P, q, A, b, lb, ub, params: Optional[Params] = None):

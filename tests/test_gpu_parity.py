@@ -506,6 +506,39 @@ def test_results_do_not_depend_on_batch_position(mods):
     np.testing.assert_array_equal(u_a[48:], u_c)
 
 
+def test_host_io_arena_round_trip(mods):
+    """The host-buffer path (BatchSCP.host_io / upload / download: one contiguous copy each way over the I/O arena)
+    gives bit-identical results to per-tensor load_inputs, and the pinned mirror holds every result of the step;
+    an obstacle batch lays out its extra inputs in the same arena."""
+    torch, scen = mods["torch"], mods["scen"]
+    cb = scen.circle_batch(64, step_lo=6, step_hi=7)
+    ref = mods["batch"].BatchSCP(64, 8, 10)
+    ref.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((64, 80)))
+    ref.controller_step()
+    ref.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+    bs = mods["batch"].BatchSCP(64, 8, 10)
+    hio = bs.host_io()
+    for k in ("x0", "u0", "veh", "poly", "dsafe"):
+        getattr(hio, k)[...] = np.asarray(getattr(cb, k)).reshape(getattr(hio, k).shape)
+    hio.u[...] = 0.0
+    bs.upload(hio)
+    bs.controller_step()
+    bs.advance_linear(scen.MECH_LIMIT, scen.DU_LIM)
+    bs.download(hio)
+    torch.cuda.synchronize()
+    for k in ("x0", "u0", "u", "U", "traj", "obj", "max_violation", "scp_iters", "ipm_iters", "status"):
+        np.testing.assert_array_equal(getattr(hio, k), host(getattr(ref, k)), err_msg=k)
+        np.testing.assert_array_equal(getattr(hio, k), host(getattr(bs, k)), err_msg=k)
+    assert hio.nbytes_in == sum(host(getattr(bs, k)).nbytes for k in ("veh", "poly", "dsafe", "x0", "u0", "u"))
+    assert int(hio.scp_iters.sum()) > 64
+    # second step straight from the host mirror (x0, u0, u are the values just read back)
+    ref.controller_step(); bs.upload(hio); bs.controller_step(); bs.download(hio); torch.cuda.synchronize()
+    np.testing.assert_array_equal(hio.u, host(ref.u))
+    ob = mods["batch"].BatchSCP(3, 1, 10, nObst=22)
+    assert ob.obst.shape == (3, 22, 10, 2) and ob.dsafe_obst.shape == (3, 1, 22)
+    assert ob.obst.data_ptr() - ob.io.data_ptr() == ob.io_layout["obst"][0] and ob.obst.is_contiguous()
+
+
 def test_work_order_and_ordered_solve(mods):
     """scpb200_work_order gives a permutation sorted by descending work; the ordered solve (longest instances first)
     returns bit-identical results to the natural pull order."""
