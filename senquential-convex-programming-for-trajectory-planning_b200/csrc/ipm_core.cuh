@@ -50,6 +50,7 @@ struct IpmCtl {
 // zero padding, the padded diagonal of S is 1.
 struct IpmMem {
     int n1, n1p, T, mc;
+    bool S_far;     // S lives in the L2-resident workspace slice, not in shared memory (long horizons): chol_factor_left
     double *S;      // [T(T+1)/2 * 64]   tile-packed lower triangle of the normal matrix / its Cholesky factor;
                     //                   (diagonal tiles replaced by their inverses after chol_invert_diag)
     double *x, *q, *rx, *dx, *tn;                    // [n1p]
@@ -337,6 +338,145 @@ SCP_FN void chol_factor(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
     }
 }
 
+// ---- left-looking variant for a factor that lives in the L2-resident workspace (long horizons, Hp = 50: 679 KB) -------------
+// The right-looking update above moves 1.8 KB per tile product through the SM's path to L2 (operands, C in, C out) and was
+// measured to be bound by exactly that (1.06 M of the 2.23 M cycles of an iteration).  Left-looking, tile column K is brought up
+// to date in one go,  S_IK -= sum_{J<K} L_IJ L_KJ'  (I = K .. T-1), with the sum ACCUMULATED IN REGISTERS over J: per product
+// two operand fragments are read (the one of tile row K is shared by all the tiles a warp works on), nothing is written; C makes
+// one round trip per tile instead of one per product.  Up to four tiles per warp and pass, so that their loads overlap.
+// Warp 0 takes the diagonal tile first and factors it while the others finish the column.  Same products, summed before they are
+// subtracted instead of one by one (rounding-level differences from chol_factor).
+#define SCP_LEFT_NT 4
+#if SCP_DEVICE_BUILD
+// NT tiles (rows I0, I0 + dI, ...) of tile column K, UJ tile columns J per chunk: every operand fragment of a chunk is requested
+// before its first product issues (2 UJ (1 + NT) loads in flight per lane) — with one J per round trip to L2 the update ran at
+// exactly one L2 latency per product (ncu: 16 % of the samples on these loads, 14 % at the barrier behind them).
+template <int NT, int UJ>
+SCP_NOINLINE_FN void warp_column_update_dev(int lane, double *S, int K, int I0, int dI, int T)
+{
+    const int ia0 = scp_frag_rowmajor(lane, 0), ia1 = scp_frag_rowmajor(lane, 1), ic = scp_frag_c(lane);
+    double acc[NT][2];
+    const double *Ap[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        acc[t][0] = acc[t][1] = 0.0;
+        const int I = I0 + t * dI;
+        Ap[t] = S + scp_tile_off(I < T ? I : K, 0) + ia0;      // tiles (I, 0), (I, 1), ... are contiguous
+    }
+    const double *Bp = S + scp_tile_off(K, 0) + ia0;
+    const int d1 = ia1 - ia0;
+    // (Measured and not kept: a predicated last chunk instead of the remainder loop, with C requested before the products —
+    // 1.07 M cycles per factorisation against 0.96 M for this version.)
+    int J = 0;
+    for (; J + UJ <= K; J += UJ) {
+        double b[UJ][2], a[NT][UJ][2];
+#pragma unroll
+        for (int u = 0; u < UJ; ++u) { b[u][0] = Bp[(J + u) * SCP_TILE2]; b[u][1] = Bp[(J + u) * SCP_TILE2 + d1]; }
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if (I0 + t * dI < T) {
+#pragma unroll
+                for (int u = 0; u < UJ; ++u) { a[t][u][0] = Ap[t][(J + u) * SCP_TILE2]; a[t][u][1] = Ap[t][(J + u) * SCP_TILE2 + d1]; }
+            }
+#pragma unroll
+        for (int u = 0; u < UJ; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+                if (I0 + t * dI < T) { scp_dmma(acc[t][0], acc[t][1], a[t][u][0], b[u][0]); scp_dmma(acc[t][0], acc[t][1], a[t][u][1], b[u][1]); }
+    }
+    for (; J < K; ++J) {
+        const double b0 = Bp[J * SCP_TILE2], b1 = Bp[J * SCP_TILE2 + d1];
+        double a0[NT], a1[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if (I0 + t * dI < T) { a0[t] = Ap[t][J * SCP_TILE2]; a1[t] = Ap[t][J * SCP_TILE2 + d1]; }
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if (I0 + t * dI < T) { scp_dmma(acc[t][0], acc[t][1], a0[t], b0); scp_dmma(acc[t][0], acc[t][1], a1[t], b1); }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+        if (I0 + t * dI < T) {
+            double2 *cp = reinterpret_cast<double2 *>(S + scp_tile_off(I0 + t * dI, K) + ic);
+            double2 c = *cp;
+            c.x -= acc[t][0]; c.y -= acc[t][1];
+            *cp = c;
+        }
+}
+#endif
+// single = true: the tile (I0, K) alone (the diagonal tile: deeper chunks); else up to SCP_LEFT_NT tiles I0, I0 + dI, ...
+SCP_FN void warp_column_update(int lane, double *S, int K, int I0, int dI, int T, bool single)
+{
+#if SCP_DEVICE_BUILD
+    if (single) warp_column_update_dev<1, 8>(lane, S, K, I0, T, T);
+    else warp_column_update_dev<SCP_LEFT_NT, 2>(lane, S, K, I0, dI, T);
+#else
+    if (lane == 0)
+        for (int t = 0; t < (single ? 1 : SCP_LEFT_NT); ++t) {
+            const int I = I0 + t * dI;
+            if (I >= T) continue;
+            double *C = S + scp_tile_off(I, K);
+            for (int r = 0; r < 8; ++r)
+                for (int c = 0; c < 8; ++c) {
+                    double acc = 0.0;
+                    for (int J = 0; J < K; ++J) {
+                        const double *A = S + scp_tile_off(I, J), *B = S + scp_tile_off(K, J);
+                        for (int k = 0; k < 8; ++k) acc += A[scp_tphys(r, k)] * B[scp_tphys(c, k)];
+                    }
+                    C[scp_tphys(r, c)] -= acc;
+                }
+        }
+#endif
+}
+
+SCP_FN void chol_factor_left(Cta &cta, const IpmMem &m, int *fixed SCP_TIMER_ARG)
+{
+    const int T = m.T;
+    double *S = m.S, *dinv = m.dinv;
+    for (int K = 0; K < T; ++K) {
+        // (a) column K up to date; its diagonal tile factored by lane 0 of warp 0 meanwhile
+        WARP_SECTION(w, nw)
+            WARP_PHASE(lane)
+                if (w == 0) warp_column_update(lane, S, K, K, T, T, true);       // the diagonal tile alone
+            WARP_PHASE_END
+            WARP_PHASE(lane)
+                if (w == 0 && lane == 0) tile_potrf(S + scp_tile_off(K, K), dinv + K * 8, fixed);
+                if (w > 0 || nw == 1) {
+                    const int nwork = nw > 1 ? nw - 1 : 1;
+                    // one tile per call, eight tile columns J per chunk (32 operand loads in flight per lane): more round trips to L2
+                    // overlap than with four tiles and two columns per chunk (measured, profiles/r02_left_looking_*)
+                    for (int I0 = K + 1 + (nw > 1 ? w - 1 : 0); I0 < T; I0 += nwork)
+                        warp_column_update(lane, S, K, I0, nwork, T, true);
+                }
+            WARP_PHASE_END
+        WARP_SECTION_END
+        CTA_SYNC
+        SCP_TIMER(4)
+        // (b) panel rows: x L_KK' = s   (as in chol_factor)
+        const double *Lkk = S + scp_tile_off(K, K);
+        const int Tr = T - K - 1;
+        CTA_PHASE(tid)
+            for (int pr = tid; pr < Tr * 8; pr += cta.nt) {
+                const int I = K + 1 + (pr >> 3), r = pr & 7;
+                double *row = S + scp_tile_off(I, K) + (r << 3);
+                const int h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { x[c] = row[h0 + c]; x[c + 4] = row[h1 + c]; }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    x[c] *= dinv[K * 8 + c];
+#pragma unroll
+                    for (int c2 = c + 1; c2 < 8; ++c2) x[c2] -= x[c] * Lkk[scp_tphys(c2, c)];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { row[h0 + c] = x[c]; row[h1 + c] = x[c + 4]; }
+            }
+        CTA_PHASE_END
+        SCP_TIMER(3)
+    }
+}
+
 // ---- solves: inverted diagonal tiles + tile-wise substitution by one warp -------------------------------------------
 // Substitution against L is a dependent chain over the n1 unknowns.  What was measured on B200 (n1p = 88, 3 CTAs per SM):
 //   * full inverse X = L^-1 (round 1): two mat-vecs per solve (1.8 k cycles each) but n1^3/6 multiply-adds and 2 T CTA
@@ -467,8 +607,123 @@ SCP_FN double trsv_col_dot(const double *S, int K, int j, const double *x)
 // in step K those lanes bring the rows of tile K up to date with the unknowns of tile K-1 (found in the previous step),
 // exchange them, and apply the inverse of the diagonal tile (an 8 x 8 mat-vec) to get the unknowns of tile K; meanwhile
 // every other thread takes the unknowns of tile K-1 out of one row further down.  Backward likewise with columns.
+#if SCP_DEVICE_BUILD
+// ---- sweeps against a factor in the L2-resident workspace (long horizons) ---------------------------------------------------
+// With the factor in shared memory a step of the sweep is bound by arithmetic and exchange inside warp 0 (the register-resident
+// variant of this routine was measured there and not kept: profiles/r02_pipelined_sweeps_experiment.txt).  With the factor in L2
+// every operand costs a round trip of ~700 cycles, and the phase version below pays two of them in sequence inside warp 0 plus
+// one in every other thread per tile column (ncu at Hp = 50: 22 % of all warp samples wait at the barrier that ends a step).  The
+// factor is constant during a sweep, so here EVERY operand of step K+1 — the rows (columns) of the off-diagonal and of the
+// inverted diagonal tile for warp 0, one row (column) of the off-diagonal tile for every other thread — is requested before the
+// barrier that ends step K, and a step touches only registers and shared memory.  Warp 0 runs nothing but the chain (all 32
+// lanes, full-mask shuffles; lanes 0-7 own the tile); thread 32 + w owns row 8 + w (forward) / column w (backward) for the whole
+// sweep; rows beyond that range (n1p > 8 + threads - 32) are handled without prefetch.  Same arithmetic as the phase version.
+SCP_FN double trsv_tree8(const double (&a)[8], const double (&x)[8])
+{
+    return ((a[0] * x[0] + a[1] * x[1]) + (a[2] * x[2] + a[3] * x[3])) + ((a[4] * x[4] + a[5] * x[5]) + (a[6] * x[6] + a[7] * x[7]));
+}
+SCP_FN void trsv_load_row(const double *tl, int r, double (&a)[8])      // row r of a tile in logical column order
+{
+    const int h0 = ((r >> 1) & 1) << 2, h1 = h0 ^ 4;
+    const double2 *row2 = reinterpret_cast<const double2 *>(tl + (r << 3));
+    const double2 r0 = row2[h0 >> 1], r1 = row2[(h0 >> 1) + 1], r2 = row2[h1 >> 1], r3 = row2[(h1 >> 1) + 1];
+    a[0] = r0.x; a[1] = r0.y; a[2] = r1.x; a[3] = r1.y; a[4] = r2.x; a[5] = r2.y; a[6] = r3.x; a[7] = r3.y;
+}
+SCP_FN void trsv_load_col(const double *tl, int c, double (&a)[8])      // column c of a tile in logical row order
+{
+    const int lo = c & 3, he = (c >> 2) << 2, ho = he ^ 4;               // rows 0,1,4,5 / rows 2,3,6,7
+    a[0] = tl[he + lo]; a[1] = tl[8 + he + lo]; a[2] = tl[16 + ho + lo]; a[3] = tl[24 + ho + lo];
+    a[4] = tl[32 + he + lo]; a[5] = tl[40 + he + lo]; a[6] = tl[48 + ho + lo]; a[7] = tl[56 + ho + lo];
+}
+SCP_FN void trsv_load_x(const double *xp, double (&x)[8])
+{
+    const double2 *x2 = reinterpret_cast<const double2 *>(xp);
+    const double2 x0 = x2[0], x1 = x2[1], x2v = x2[2], x3 = x2[3];
+    x[0] = x0.x; x[1] = x0.y; x[2] = x1.x; x[3] = x1.y; x[4] = x2v.x; x[5] = x2v.y; x[6] = x3.x; x[7] = x3.y;
+}
+SCP_FN void chol_solve_far(Cta &cta, const IpmMem &m, double *v, bool have_y)
+{
+    const int T = m.T, n1p = m.n1p;
+    const double *S = m.S;
+    const int tid = (int)threadIdx.x, lane = tid & 31, nw = cta.nt >> 5;
+    const bool crit = tid < 32;
+    const int l8 = lane & 7;
+    const int nwork = nw > 1 ? cta.nt - 32 : 24;         // a single-warp CTA: lanes 8 .. 31 take the rows beyond after the chain
+    const int wid = nw > 1 ? tid - 32 : lane - 8;        // < 0: not a worker
+    for (int dir = have_y ? 1 : 0; dir < 2; ++dir) {
+        if (dir == 1) {
+            if (tid == 0) v[n1p - 1] = 0.0;              // the right-hand-side row is not part of the system
+            __syncthreads();
+        }
+        // the worker's own row (forward: 8 + wid, beyond tile K while >= 8 (K + 1)) or column (backward: wid, beyond while < 8 K)
+        const int wi = dir == 0 ? 8 + wid : wid;
+        const bool wown = wid >= 0 && wi < n1p;
+        double xk = 0.0, a[8], d[8], wa[8];
+        if (crit) {
+            const int K0 = dir == 0 ? 0 : T - 1;
+            if (dir == 0) trsv_load_row(S + scp_tile_off(K0, K0), l8, d); else trsv_load_col(S + scp_tile_off(K0, K0), l8, d);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = 0.0;
+        }
+        if (wown && T > 1) {                             // operands of step 1
+            if (dir == 0) { if (wi >= 16) trsv_load_row(S + scp_tile_off(wi >> 3, 0), wi & 7, wa); }
+            else { if (wi < (T - 2) * 8) trsv_load_col(S + scp_tile_off(T - 1, wi >> 3), wi & 7, wa); }
+        }
+        for (int step = 0; step < T; ++step) {
+            const int K = dir == 0 ? step : T - 1 - step;    // tile whose unknowns this step finds
+            const int Kp = dir == 0 ? K - 1 : K + 1;         // tile found in the previous step
+            const int Kn = dir == 0 ? K + 1 : K - 1;         // tile of the next step
+            if (crit) {
+                double r = v[K * 8 + l8];
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = __shfl_sync(0xffffffffu, xk, c);
+                if (step > 0) r -= trsv_tree8(a, x);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = __shfl_sync(0xffffffffu, r, c);
+                xk = trsv_tree8(d, x);
+                if (lane < 8) v[K * 8 + lane] = xk;
+                if (step + 1 < T) {
+                    if (dir == 0) {
+                        trsv_load_row(S + scp_tile_off(Kn, K), l8, a);
+                        trsv_load_row(S + scp_tile_off(Kn, Kn), l8, d);
+                    } else {
+                        trsv_load_col(S + scp_tile_off(K, Kn), l8, a);
+                        trsv_load_col(S + scp_tile_off(Kn, Kn), l8, d);
+                    }
+                }
+            }
+            if (wid >= 0 && step > 0) {
+                const double *xp = v + Kp * 8;
+                const bool act = dir == 0 ? wi >= (K + 1) * 8 : wi < K * 8;
+                if (wown && act) {
+                    double x[8];
+                    trsv_load_x(xp, x);
+                    v[wi] -= trsv_tree8(wa, x);
+                }
+                // rows / columns beyond the one-per-thread range (not prefetched)
+                if (dir == 0) {
+                    for (int i = wi + nwork; i < n1p; i += nwork)
+                        if (i >= (K + 1) * 8) v[i] -= trsv_row_dot(S, i, Kp, xp);
+                } else {
+                    for (int j = wi + nwork; j < K * 8; j += nwork) v[j] -= trsv_col_dot(S, Kp, j, xp);
+                }
+            }
+            if (wown && step + 1 < T) {                      // the worker's operand of step K+1: tile column K (forward) / tile row K (backward)
+                if (dir == 0) { if (wi >= (Kn + 1) * 8) trsv_load_row(S + scp_tile_off(wi >> 3, K), wi & 7, wa); }
+                else { if (wi < Kn * 8) trsv_load_col(S + scp_tile_off(K, wi >> 3), wi & 7, wa); }
+            }
+            __syncthreads();
+        }
+    }
+}
+#endif
+
 SCP_FN void chol_solve(Cta &cta, const IpmMem &m, double *v, bool have_y)
 {
+#if SCP_DEVICE_BUILD
+    if (m.S_far) { chol_solve_far(cta, m, v, have_y); return; }
+#endif
     const int T = m.T, n1p = m.n1p;
     const double *S = m.S;
     const int nwork = cta.nt - 8;                        // threads that work on the rows / columns beyond the current tile
@@ -653,7 +908,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                            return d;
                        } SCP_TIMER_PASS);
         SCP_TIMER(1)
-        chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
+        if (m.S_far) chol_factor_left(cta, m, fixed_p SCP_TIMER_PASS); else chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
         chol_invert_diag(cta, m, m.x);
         chol_solve(cta, m, m.x, true);
         SCP_TIMER(8)
@@ -807,7 +1062,7 @@ SCP_FN void ipm_solve(Cta &cta, Op &op, const IpmMem &m, const IpmCtl &ctl, IpmR
                            return d;
                        } SCP_TIMER_PASS);
         SCP_TIMER(1)
-        chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
+        if (m.S_far) chol_factor_left(cta, m, fixed_p SCP_TIMER_PASS); else chol_factor(cta, m, fixed_p SCP_TIMER_PASS);
         chol_invert_diag(cta, m, m.dx);
         SCP_TIMER(5)
 

@@ -880,6 +880,7 @@ SCP_HDFN void ipm_carve(ScpBump &bp, IpmMem &m, int n1, int mc, int red_doubles 
 SCP_HDFN void ipm_carve_big(ScpBump &bp, IpmMem &m)
 {
     m.S = bp.take((size_t)(m.T * (m.T + 1) / 2) * SCP_TILE2);
+    m.S_far = !bp.last_shared;
 }
 
 struct ScpMem {

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(NT, 3) k_bench(long long *out, int reps, int p
     extern __shared__ double sh[];
     Cta cta = {NT};
     IpmMem m;
-    m.n1 = N1; m.n1p = ipm_padded(N1); m.T = m.n1p / 8; m.mc = 0;
+    m.S_far = false; m.n1 = N1; m.n1p = ipm_padded(N1); m.T = m.n1p / 8; m.mc = 0;
     double *p = sh;
     m.S = p; p += (m.T * (m.T + 1) / 2) * 64;
     m.dinv = p; p += m.n1p;
