@@ -208,6 +208,41 @@ def test_launch_shape_follows_dimensions_and_every_cta_width_agrees(mods, monkey
     monkeypatch.delenv("SCPB200_THREADS", raising=False)
 
 
+def test_long_horizon_routines_on_short_horizon_goldens(mods, monkeypatch):
+    """chol_factor_left / chol_solve_far (the versions of the factorisation and of the triangular sweeps for a factor in the
+    L2-resident workspace, Hp = 50 in production) on the Hp = 10 / 20 goldens: SCPB200_FORCE_GLOBAL_S pushes the normal
+    matrix out of shared memory; every CTA width incl. a single warp (the rows beyond the current tile then belong to lanes
+    8..31 of the same warp) and 64 threads (more rows than threads: the not-prefetched remainder).  Teacher-forced against the
+    reference's golden solution (1e-6) and against the shared-memory path (rounding level)."""
+    for fname in ("circle8_hp10_step6.npz", "circle8_hp10_step10.npz", "circle8_hp20_step5.npz"):
+        if not os.path.exists(os.path.join(GOLDEN, fname)):
+            continue
+        G = load_golden(fname)
+        nit = min(4, int(G["scp_iters"]))
+        monkeypatch.delenv("SCPB200_FORCE_GLOBAL_S", raising=False)
+        monkeypatch.delenv("SCPB200_THREADS", raising=False)
+        bs = make_batch(mods, G, B=nit, max_scp_iter=1)
+        bs.load_inputs(u=G["prev_u"][:nit])
+        assert bs.plan()["S_in_shared"]
+        bs.controller_step()
+        u_shared = host(bs.u).copy()
+        monkeypatch.setenv("SCPB200_FORCE_GLOBAL_S", "1")
+        for forced in (32, 64, 128, 256, 512):
+            monkeypatch.setenv("SCPB200_THREADS", str(forced))
+            bs = make_batch(mods, G, B=nit, max_scp_iter=1)
+            bs.load_inputs(u=G["prev_u"][:nit])
+            pl = bs.plan()
+            assert not pl["S_in_shared"] and pl["threads"] == forced, (fname, pl)
+            bs.controller_step()
+            u = host(bs.u)
+            assert (host(bs.status) & (mods["capi"].ST_QP_MAXITER | mods["capi"].ST_QP_PIVOT)).max() == 0
+            for it in range(nit):
+                assert np.abs(u[it] - G["x"][it][:-1]).max() < 1e-6, (fname, forced, it)
+            assert np.abs(u - u_shared).max() < 1e-7, (fname, forced)
+    monkeypatch.delenv("SCPB200_FORCE_GLOBAL_S", raising=False)
+    monkeypatch.delenv("SCPB200_THREADS", raising=False)
+
+
 @pytest.mark.parametrize("fname", NOT50)
 def test_scp_kernel_free_running(mods, fname):
     G = load_golden(fname)
