@@ -259,7 +259,24 @@ def strong_leg(args, mods, dev, rank, world, flush, barrier, total=4096):
         asm_frac = assembly_bytes_per_qp(args.nveh, args.hp) * B / (ams * 1e-3) / 1e9 / peaks["hbm_gbs"]
         del out
     c = cnt.cpu()
-    return float(np.sum(ms)) * 1e-3, int(c[0]), int(c[1]), B, float(np.median(ms)), asm_frac
+    # the same shard and steps through the rollout entry (all timed MPC steps of every instance in ONE launch: no step of the
+    # shard waits for its longest chain of QPs, which is what bounds the per-step line at 4096 / N instances per GPU)
+    bs.load_inputs(x0=cb.x0, u0=cb.u0, veh=cb.veh, poly=cb.poly, dsafe=cb.dsafe, u=np.zeros((B, args.nveh * args.hp)))
+    bs.params.noise_counter = 0
+    if args.warmup > 0:
+        bs.rollout(args.warmup, uMax, duLim)
+    torch.cuda.synchronize(dev)
+    barrier()
+    bs.params.noise_counter = args.warmup
+    flush.zero_()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    ro = bs.rollout(args.steps, uMax, duLim)
+    r1.record()
+    barrier()
+    ro_t = r0.elapsed_time(r1) * 1e-3
+    ro_qps = int(ro["qp_total"].sum().item())
+    return float(np.sum(ms)) * 1e-3, int(c[0]), int(c[1]), B, float(np.median(ms)), asm_frac, ro_t, ro_qps
 
 
 def sharding_check(args, mods, dev, rank, world, nsample=64, nsteps=2):
@@ -465,20 +482,21 @@ def run_product(args):
         del outbuf
 
     # ---------------- north-star strong configuration + sharding bit-identity ----------------
-    st_t, st_qps, st_ipm, st_B, st_p50, st_asm = strong_leg(args, mods, dev, rank, world, flush, barrier, total=args.strong_total)
+    st_t, st_qps, st_ipm, st_B, st_p50, st_asm, st_ro_t, st_ro_qps = strong_leg(args, mods, dev, rank, world, flush, barrier, total=args.strong_total)
     shard = sharding_check(args, mods, dev, rank, world)
 
     # ---------------- reduce over ranks ----------------
     t_max, qps_all, e2e_max, e2e_all = t_dev, qps_rank, t_e2e, e2e_qps
     st_t_max, st_qps_all, st_ipm_all = st_t, st_qps, st_ipm
+    st_ro_t_max, st_ro_qps_all = st_ro_t, st_ro_qps
     roll_t_max, roll_qps_all, roll_ipm_all = t_roll, roll_qps, roll_ipm
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e, t_roll, st_t], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_dev, t_e2e, t_roll, st_t, st_ro_t], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank, roll_qps, roll_ipm, st_qps, st_ipm], dtype=torch.int64, device=dev)
+        cc = torch.tensor([qps_rank, e2e_qps, ipm_rank, roll_qps, roll_ipm, st_qps, st_ipm, st_ro_qps], dtype=torch.int64, device=dev)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        t_max, e2e_max, roll_t_max, st_t_max = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
-        qps_all, e2e_all, ipm_all, roll_qps_all, roll_ipm_all, st_qps_all, st_ipm_all = (int(v) for v in cc)
+        t_max, e2e_max, roll_t_max, st_t_max, st_ro_t_max = (float(v) for v in tt)
+        qps_all, e2e_all, ipm_all, roll_qps_all, roll_ipm_all, st_qps_all, st_ipm_all, st_ro_qps_all = (int(v) for v in cc)
         # the optional all-gather of trajectories / statistics, off the timed path
         gathered = [torch.empty_like(bs.U) for _ in range(world)]
         dist.all_gather(gathered, bs.U)
@@ -524,8 +542,11 @@ def run_product(args):
                                   "scaling": "strong", "qps_total": st_qps_all, "ipm_iterations_total": st_ipm_all,
                                   "roofline_frac": float(fit * st_ipm_all / world / st_t_max / 1e12 / fp64_pk),
                                   "assembly_frac_hbm_rank0": st_asm,
+                                  "rollout_value": st_ro_qps_all / st_ro_t_max, "rollout_ms_per_step": 1e3 * st_ro_t_max / args.steps,
+                                  "rollout_qps_total": st_ro_qps_all,
                                   "note": "BASELINE.json north star: 4096 scenarios in total, contiguous shards of 4096/N per GPU, the same "
-                                          "closed-loop MPC steps (max over ranks of the summed CUDA-event step times)"},
+                                          "closed-loop MPC steps (max over ranks of the summed CUDA-event step times); rollout_value: the same shards and "
+                                          "steps through scpb200_mpc_rollout (one launch per rank, bit-identical results)"},
             "sharding_bitwise_ok": shard,
             "rollout": {"value": roll_qps_all / roll_t_max, "unit": UNIT, "ms_per_step": 1e3 * roll_t_max / args.steps,
                         "steps_per_launch": args.steps, "qps_total": roll_qps_all, "ipm_iterations_total": roll_ipm_all,
